@@ -1,0 +1,121 @@
+/*
+ * vbkkt.h -- C ABI of libvbkkt.so, the B200 (sm_100a) implementation of the per-iteration KKT step of
+ * Vanderbei's interior-point LP codes.  Plain C types only; every pointer is HOST memory unless the
+ * name says `_dev`.  There is no CPU path: every numeric entry point prints a message and exit(1)s
+ * when no CUDA device is usable (the reference's own error convention, src/common/myalloc.h:17-24).
+ *
+ * Three groups:
+ *   B1  the reference's plugin symbols, exact signatures, so that the reference's C driver links
+ *       libvbkkt.so in place of ldlt.o and the linalg.o member of common.a (src/ipo/makefile:49-64);
+ *   B2  the METHOD plugin `solver` (same signature/stdout/status as src/ipo/hsd.c:27, intpt.c:33),
+ *       device-resident; exported as vbk_solver_hsd / vbk_solver_intpt here and as plain `solver`
+ *       by the two one-function shims libvbkkt_hsd.so / libvbkkt_intpt.so;
+ *   H   a handle-based API (no reference equivalent: the reference has one process-global factor
+ *       object, src/ipo/ldlt.c:108-120) for tests, the batch driver and the bench.
+ */
+#ifndef VBKKT_H
+#define VBKKT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * B1 -- replaces src/ipo/ldlt.c (declared in src/ipo/ldlt.h:1-20 and src/common/lp.h:213-239)
+ * ---------------------------------------------------------------------------------------------- */
+/* ldlt.h:1-13.  First call: symbolic analysis of K = [-diag(dn) A^T; A diag(dm)] and upload of the
+ * matrix (pointers are retained like the reference does, ldlt.c:140-160); every call: numeric LDL^T. */
+void ldltfac(int m, int n, int *kA, int *iA, double *A, double *dn, double *dm,
+             int *kAt, int *iAt, double *At, int verbose);
+/* ldlt.h:15-20.  Solves K [dx;dy] = [dx;dy] in place with iterative refinement (ldlt.c:327-425). */
+void forwardbackward(double *Dn, double *Dm, double *dx, double *dy);
+/* lp.h:236-239 / ldlt.c:507-513: releases the process-global factor object. */
+void inv_clo(void);
+
+/* replaces the ipo-relevant part of src/common/linalg.c (declared in src/common/linalg.h:1-8) */
+double dotprod(double *x, double *y, int n);                                   /* linalg.c:17-25  */
+void   smx(int m, int n, double *a, int *ka, int *ia, double *x, double *y);   /* linalg.c:62-70  */
+void   atnum(int m, int n, int *ka, int *ia, double *a,
+             int *kat, int *iat, double *at);                                  /* linalg.c:75-103 */
+double maxv(double *x, int n);                                                 /* linalg.c:108-116 */
+
+/* ------------------------------------------------------------------------------------------------
+ * B2 -- replaces the METHOD object (src/ipo/hsd.c:27 / src/ipo/intpt.c:33; caller: solve.c:237)
+ * ---------------------------------------------------------------------------------------------- */
+int vbk_solver_hsd(int m, int n, int nz, int *iA, int *kA, double *A, double *b, double *c, double f,
+                   double *x, double *y, double *w, double *z);
+int vbk_solver_intpt(int m, int n, int nz, int *iA, int *kA, double *A, double *b, double *c, double f,
+                     double *x, double *y, double *w, double *z);
+
+/* ------------------------------------------------------------------------------------------------
+ * H -- handle API
+ * ---------------------------------------------------------------------------------------------- */
+#define VBK_MODE_STRICT 0   /* order-faithful, unfused: reproduces the reference bit for bit */
+#define VBK_MODE_FAST   1   /* tree reductions / supernodal panels: tolerance parity          */
+
+/* process-wide defaults used by the B1/B2 symbols (also read once from $VBK_MODE=strict|fast and
+ * $VBK_DEVICE=<ordinal>) */
+void vbk_set_mode(int mode);
+int  vbk_get_mode(void);
+void vbk_set_device(int device);
+int  vbk_device_count(void);          /* 0 when no usable CUDA device (never exits) */
+const char *vbk_version(void);
+
+typedef struct vbk_kkt vbk_kkt;
+/* device < 0: host-side symbolic analysis only (numeric calls on such a handle exit(1)) */
+vbk_kkt *vbk_kkt_create(int device, int mode);
+void     vbk_kkt_destroy(vbk_kkt *h);
+/* ldlt-space arguments exactly as ldltfac: A is m x n CSC, At its transpose */
+void vbk_kkt_analyze(vbk_kkt *h, int m, int n, const int *kA, const int *iA, const double *A,
+                     const int *kAt, const int *iAt, const double *At);
+void vbk_kkt_factor(vbk_kkt *h, const double *dn, const double *dm);
+int  vbk_kkt_solve(vbk_kkt *h, const double *Dn, const double *Dm, double *dx, double *dy);
+/* device-pointer variants (no host traffic); all on the handle's stream, asynchronous */
+void vbk_kkt_factor_dev(vbk_kkt *h, const double *dn_dev, const double *dm_dev);
+int  vbk_kkt_solve_dev(vbk_kkt *h, const double *Dn_dev, const double *Dm_dev, double *dx_dev, double *dy_dev);
+/* one raw forward/diagonal/backward sweep (ldlt.c:433-505) on a permuted host vector of length m+n */
+int  vbk_kkt_rawsolve(vbk_kkt *h, double *zperm);
+void vbk_kkt_sync(vbk_kkt *h);
+void *vbk_kkt_stream(vbk_kkt *h);     /* cudaStream_t */
+
+/* symbolic results (valid after analyze; host memory owned by the handle) */
+int        vbk_kkt_dim(const vbk_kkt *h);
+long long  vbk_kkt_lnz(const vbk_kkt *h);
+int        vbk_kkt_denwin(const vbk_kkt *h);
+int        vbk_kkt_pdf(const vbk_kkt *h);
+double     vbk_kkt_narth(const vbk_kkt *h);
+int        vbk_kkt_nlevels(const vbk_kkt *h);
+int        vbk_kkt_nsupernodes(const vbk_kkt *h);
+const int *vbk_kkt_perm(const vbk_kkt *h);
+const int *vbk_kkt_iperm(const vbk_kkt *h);
+const int *vbk_kkt_kAAt(const vbk_kkt *h);
+const int *vbk_kkt_iAAt(const vbk_kkt *h);
+/* numeric results: copies L values [lnz], diag [dim], mark [dim] to host (any may be NULL) */
+void   vbk_kkt_get_factor(vbk_kkt *h, double *L, double *diag, int *mark);
+double vbk_kkt_epsdiag(vbk_kkt *h);
+int    vbk_kkt_ndep(vbk_kkt *h);
+int    vbk_kkt_last_passes(const vbk_kkt *h);
+long long vbk_kkt_launches(const vbk_kkt *h);
+
+/* profile of the last vbk_solver_* / vbk_solve_lp call (seconds; GPU work bracketed by stream syncs) */
+typedef struct vbk_profile {
+    double total_s, setup_s, factor_s, solve_s;
+    long long factor_calls, solve_calls, rawsolve_calls, kernel_launches, refine_passes;
+    int iterations, N;
+    long long lnz;
+    double narth;
+} vbk_profile;
+/* method: 0 = hsd, 1 = intpt.  Like vbk_solver_* but on an explicit device/mode, const inputs, no
+ * ownership quirks (w,z are not touched), optional profile. */
+int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const int *iA, const int *kA,
+                 const double *A, const double *b, const double *c, double f,
+                 double *x, double *y, vbk_profile *prof);
+
+/* Test hook (mirrors the oracle's kko_capture): copy the KKT-step inputs E[m], D[n], rhs_y[m], rhs_x[n]
+ * and outputs sol_y[m], sol_x[n] of iteration `iter` of the next solve into host buffers; iter<0 = off. */
+void vbk_capture(int iter, double *E, double *D, double *rhs_y, double *rhs_x, double *sol_y, double *sol_x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBKKT_H */

@@ -1,0 +1,212 @@
+// vbk_capi.cu -- extern "C" surface of libvbkkt.so (declared in include/vbkkt.h).
+#include "../../include/vbkkt.h"
+#include "vbk_kkt.h"
+#include "vbk_linalg.h"
+#include "vbk_solver.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+using namespace vbk;
+
+struct vbk_kkt {
+    Kkt impl;
+    vbk_kkt(int device, int mode) : impl(device, mode) {}
+};
+
+namespace {
+
+int g_mode = -1, g_device = -1;
+void read_env_once()
+{
+    if (g_mode < 0) {
+        const char* e = std::getenv("VBK_MODE");
+        g_mode = (e && std::strcmp(e, "fast") == 0) ? VBK_MODE_FAST : VBK_MODE_STRICT;
+    }
+    if (g_device < 0) {
+        const char* e = std::getenv("VBK_DEVICE");
+        g_device = e ? std::atoi(e) : 0;
+    }
+}
+
+// the reference's one-factor-object-per-process state (ldlt.c:108-120), bound to handle 0
+std::unique_ptr<Kkt> g_kkt;
+std::unique_ptr<LinalgContext> g_la;
+const int* g_kA = nullptr; const int* g_iA = nullptr; const double* g_A = nullptr;
+const int* g_kAt = nullptr; const int* g_iAt = nullptr; const double* g_At = nullptr;
+DevArray<double> g_vx, g_vy;
+
+LinalgContext& linalg()
+{
+    read_env_once();
+    if (!g_la) g_la.reset(new LinalgContext(g_device, g_mode));
+    return *g_la;
+}
+
+}  // namespace
+
+extern "C" {
+
+void vbk_set_mode(int mode) { g_mode = mode; }
+int vbk_get_mode(void) { read_env_once(); return g_mode; }
+void vbk_set_device(int device) { g_device = device; }
+int vbk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char* vbk_version(void)
+{
+#ifdef VBK_EMU
+    return "vbkkt 0.1 (host emulation TEST build - not the product)";
+#else
+    return "vbkkt 0.1 (sm_100a)";
+#endif
+}
+
+// ---------------------------------------------------------------------------------------- B1
+void ldltfac(int m, int n, int* kA, int* iA, double* A, double* dn, double* dm,
+             int* kAt, int* iAt, double* At, int verbose)
+{
+    (void)verbose;
+    read_env_once();
+    if (!g_kkt) {
+        g_kkt.reset(new Kkt(g_device, g_mode));
+        g_kkt->analyze(m, n, kA, iA, A, kAt, iAt, At);
+        g_kA = kA; g_iA = iA; g_A = A; g_kAt = kAt; g_iAt = iAt; g_At = At;
+    }
+    g_kkt->factor_host(dn, dm);
+}
+
+void forwardbackward(double* Dn, double* Dm, double* dx, double* dy)
+{
+    if (!g_kkt) { std::fprintf(stderr, "vbkkt: forwardbackward() before ldltfac()\n"); std::exit(1); }
+    g_kkt->solve_host(Dn, Dm, dx, dy);
+}
+
+void inv_clo(void)
+{
+    g_kkt.reset();
+    g_kA = g_iA = g_kAt = g_iAt = nullptr;
+    g_A = g_At = nullptr;
+}
+
+double dotprod(double* x, double* y, int n) { return linalg().dotprod_host(x, y, n); }
+double maxv(double* x, int n) { return linalg().maxv_host(x, n); }
+void atnum(int m, int n, int* ka, int* ia, double* a, int* kat, int* iat, double* at)
+{
+    linalg().atnum_host(m, n, ka, ia, a, kat, iat, at);
+}
+void smx(int m, int n, double* a, int* ka, int* ia, double* x, double* y)
+{
+    // the matrix ldltfac captured is already resident in gather form: only the vectors move
+    if (g_kkt && a == g_A && ka == g_kA && ia == g_iA && m == g_kkt->sym().m && n == g_kkt->sym().n) {
+        cudaStream_t s = g_kkt->stream();
+        g_vx.upload(x, n, s); g_vy.alloc(m);
+        g_kkt->spmv_A(g_vx.p, g_vy.p);
+        g_vy.download(y, m, s);
+        VBK_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
+    if (g_kkt && a == g_At && ka == g_kAt && ia == g_iAt && m == g_kkt->sym().n && n == g_kkt->sym().m) {
+        cudaStream_t s = g_kkt->stream();
+        g_vx.upload(x, n, s); g_vy.alloc(m);
+        g_kkt->spmv_At(g_vx.p, g_vy.p);
+        g_vy.download(y, m, s);
+        VBK_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
+    linalg().smx_host(m, n, a, ka, ia, x, y);
+}
+
+// ---------------------------------------------------------------------------------------- B2
+int vbk_solver_hsd(int m, int n, int nz, int* iA, int* kA, double* A, double* b, double* c, double f,
+                   double* x, double* y, double* w, double* z)
+{
+    read_env_once();
+    int st = solver_hsd(g_device, g_mode, m, n, nz, iA, kA, A, b, c, f, x, y, nullptr);
+    std::free(w); std::free(z);       // the reference's plugins free these (hsd.c:290-291)
+    return st;
+}
+int vbk_solver_intpt(int m, int n, int nz, int* iA, int* kA, double* A, double* b, double* c, double f,
+                     double* x, double* y, double* w, double* z)
+{
+    read_env_once();
+    int st = solver_intpt(g_device, g_mode, m, n, nz, iA, kA, A, b, c, f, x, y, nullptr);
+    std::free(w); std::free(z);       // intpt.c:244-245
+    return st;
+}
+
+int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const int* iA, const int* kA,
+                 const double* A, const double* b, const double* c, double f,
+                 double* x, double* y, vbk_profile* prof)
+{
+    SolveProfile p;
+    int st = method == 0 ? solver_hsd(device, mode, m, n, nz, iA, kA, A, b, c, f, x, y, prof ? &p : nullptr)
+                         : solver_intpt(device, mode, m, n, nz, iA, kA, A, b, c, f, x, y, prof ? &p : nullptr);
+    if (prof) {
+        prof->total_s = p.total_s; prof->setup_s = p.setup_s; prof->factor_s = p.factor_s; prof->solve_s = p.solve_s;
+        prof->factor_calls = p.factor_calls; prof->solve_calls = p.solve_calls; prof->rawsolve_calls = p.rawsolve_calls;
+        prof->kernel_launches = p.kernel_launches; prof->refine_passes = p.refine_passes;
+        prof->iterations = p.iterations; prof->N = p.N; prof->lnz = p.lnz; prof->narth = p.narth;
+    }
+    return st;
+}
+
+void vbk_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x)
+{
+    set_capture(iter, E, D, rhs_y, rhs_x, sol_y, sol_x);
+}
+
+// ---------------------------------------------------------------------------------------- H
+vbk_kkt* vbk_kkt_create(int device, int mode) { return new vbk_kkt(device, mode); }
+void vbk_kkt_destroy(vbk_kkt* h) { delete h; }
+void vbk_kkt_analyze(vbk_kkt* h, int m, int n, const int* kA, const int* iA, const double* A,
+                     const int* kAt, const int* iAt, const double* At)
+{
+    h->impl.analyze(m, n, kA, iA, A, kAt, iAt, At);
+}
+void vbk_kkt_factor(vbk_kkt* h, const double* dn, const double* dm) { h->impl.factor_host(dn, dm); }
+int vbk_kkt_solve(vbk_kkt* h, const double* Dn, const double* Dm, double* dx, double* dy)
+{
+    return h->impl.solve_host(Dn, Dm, dx, dy);
+}
+void vbk_kkt_factor_dev(vbk_kkt* h, const double* dn, const double* dm) { h->impl.factor_dev(dn, dm); }
+int vbk_kkt_solve_dev(vbk_kkt* h, const double* Dn, const double* Dm, double* dx, double* dy)
+{
+    return h->impl.solve_dev(Dn, Dm, dx, dy);
+}
+int vbk_kkt_rawsolve(vbk_kkt* h, double* zperm)
+{
+    Kkt& k = h->impl;
+    const size_t N = (size_t)k.sym().N;
+    VBK_CUDA(cudaMemcpyAsync(k.zbuf(), zperm, 8 * N, cudaMemcpyHostToDevice, k.stream()));
+    k.rawsolve_dev();
+    VBK_CUDA(cudaMemcpyAsync(zperm, k.zbuf(), 8 * N, cudaMemcpyDeviceToHost, k.stream()));
+    VBK_CUDA(cudaStreamSynchronize(k.stream()));
+    return 1;
+}
+void vbk_kkt_sync(vbk_kkt* h) { VBK_CUDA(cudaStreamSynchronize(h->impl.stream())); }
+void* vbk_kkt_stream(vbk_kkt* h) { return (void*)(size_t)h->impl.stream(); }
+
+int vbk_kkt_dim(const vbk_kkt* h) { return h->impl.sym().N; }
+long long vbk_kkt_lnz(const vbk_kkt* h) { return h->impl.sym().lnz(); }
+int vbk_kkt_denwin(const vbk_kkt* h) { return h->impl.sym().denwin; }
+int vbk_kkt_pdf(const vbk_kkt* h) { return h->impl.sym().pdf; }
+double vbk_kkt_narth(const vbk_kkt* h) { return h->impl.sym().narth; }
+int vbk_kkt_nlevels(const vbk_kkt* h) { return h->impl.sym().nlevels; }
+int vbk_kkt_nsupernodes(const vbk_kkt* h) { return (int)h->impl.sym().sn_ptr.size() - 1; }
+const int* vbk_kkt_perm(const vbk_kkt* h) { return h->impl.sym().perm.data(); }
+const int* vbk_kkt_iperm(const vbk_kkt* h) { return h->impl.sym().iperm.data(); }
+const int* vbk_kkt_kAAt(const vbk_kkt* h) { return h->impl.sym().kL.data(); }
+const int* vbk_kkt_iAAt(const vbk_kkt* h) { return h->impl.sym().iL.data(); }
+void vbk_kkt_get_factor(vbk_kkt* h, double* L, double* diag, int* mark) { h->impl.download_factor(L, diag, mark); }
+double vbk_kkt_epsdiag(vbk_kkt* h) { return h->impl.epsdiag(); }
+int vbk_kkt_ndep(vbk_kkt* h) { return h->impl.ndep(); }
+int vbk_kkt_last_passes(const vbk_kkt* h) { return h->impl.stats.last_passes; }
+long long vbk_kkt_launches(const vbk_kkt* h) { return h->impl.stats.kernel_launches; }
+
+}  // extern "C"

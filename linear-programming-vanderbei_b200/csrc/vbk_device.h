@@ -1,0 +1,44 @@
+// vbk_device.h -- thin layer between the kernels and the CUDA toolchain.
+//
+// Product build: nvcc, sm_100a, real CUDA runtime.  The -DVBK_EMU branch exists only so that the
+// CPU-only unit tests (tests/emu) can run the same kernel sources on tiny inputs; it is never part
+// of libvbkkt.so.
+#pragma once
+
+#ifdef VBK_EMU
+#include "cuda_emu.h"
+#define VBK_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu::launch(dim3(grid), dim3(block), (smem), [&] { kernel(__VA_ARGS__); })
+#define VBK_DYN_SMEM(ptrname) unsigned char* ptrname = emu::dyn_smem()
+#define VBK_GRID_SYNC() emu_grid_sync()
+#else
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#define VBK_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define VBK_DYN_SMEM(ptrname) extern __shared__ __align__(16) unsigned char ptrname[]
+#endif
+
+// The reference's error convention is "print and exit(1)" (src/common/myalloc.h:17-24); a CUDA
+// failure in the drop-in does the same so that no silent CPU path can ever be taken.
+#define VBK_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            std::fprintf(stderr, "vbkkt: CUDA error %s at %s:%d: %s\n", #call, __FILE__,   \
+                         __LINE__, cudaGetErrorString(e_));                                 \
+            std::exit(1);                                                                   \
+        }                                                                                   \
+    } while (0)
+
+#define VBK_CHECK_LAUNCH() VBK_CUDA(cudaGetLastError())
+
+// volatile (L1-bypassing, non-cached) load used by the dataflow waits
+__device__ __forceinline__ int vbk_ld_volatile(const int* p) {
+#ifdef VBK_EMU
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+    return *reinterpret_cast<const volatile int*>(p);
+#endif
+}

@@ -1,0 +1,330 @@
+// vbk_kkt.cu -- host orchestration of the device-resident factor object (see vbk_kkt.h).
+#include "vbk_kkt.h"
+#include "vbk_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace vbk {
+
+namespace {
+
+// row-wise view of a CSC matrix, entries of each row in ascending column order: the order in which
+// the reference's scatter-form smx (linalg.c:62-70) accumulates into y[row]
+void csc_to_rows(int nrows, int ncols, const int* kA, const int* iA, const double* A,
+                 std::vector<int>& ptr, std::vector<int>& idx, std::vector<double>& val)
+{
+    const int nz = kA[ncols];
+    ptr.assign(nrows + 1, 0);
+    for (int k = 0; k < nz; ++k) ptr[iA[k] + 1]++;
+    for (int r = 0; r < nrows; ++r) ptr[r + 1] += ptr[r];
+    idx.assign(nz, 0);
+    val.assign(nz, 0.0);
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int j = 0; j < ncols; ++j)
+        for (int k = kA[j]; k < kA[j + 1]; ++k) {
+            int dst = fill[iA[k]]++;
+            idx[dst] = j;
+            val[dst] = A[k];
+        }
+}
+
+}  // namespace
+
+Kkt::Kkt(int device, int mode) : device_(device), mode_(mode)
+{
+    debug_ = std::getenv("VBK_DEBUG") != nullptr;
+    if (device_ < 0) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= device_) {
+        std::fprintf(stderr, "vbkkt: no CUDA device %d available (%s); this library has no CPU path\n",
+                     device_, e != cudaSuccess ? cudaGetErrorString(e) : "device count too small");
+        std::exit(1);
+    }
+    VBK_CUDA(cudaSetDevice(device_));
+    cudaDeviceProp prop;
+    VBK_CUDA(cudaGetDeviceProperties(&prop, device_));
+    num_sms_ = prop.multiProcessorCount;
+    VBK_CUDA(cudaStreamCreate(&stream_));
+    VBK_CUDA(cudaMallocHost((void**)&pin_bits_, sizeof(unsigned long long) * S_COUNT));
+    VBK_CUDA(cudaMallocHost((void**)&pin_scal_, sizeof(double) * S_COUNT));
+    VBK_CUDA(cudaMallocHost((void**)&pin_cnt_, sizeof(int) * C_COUNT));
+}
+
+Kkt::~Kkt()
+{
+    if (device_ < 0) return;
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    if (pin_bits_) cudaFreeHost(pin_bits_);
+    if (pin_scal_) cudaFreeHost(pin_scal_);
+    if (pin_cnt_) cudaFreeHost(pin_cnt_);
+#ifndef VBK_EMU
+    if (stream_) cudaStreamDestroy(stream_);
+#endif
+}
+
+void Kkt::require_device(const char* what) const
+{
+    if (device_ < 0) {
+        std::fprintf(stderr, "vbkkt: %s needs a CUDA device; this handle was created for host analysis only\n", what);
+        std::exit(1);
+    }
+    if (!analyzed_) {
+        std::fprintf(stderr, "vbkkt: %s called before analyze()\n", what);
+        std::exit(1);
+    }
+}
+
+int Kkt::vec_grid(long long n) const
+{
+    long long g = (n + kVecThreads - 1) / kVecThreads;
+    long long cap = (long long)num_sms_ * 8;
+    if (g < 1) g = 1;
+    return (int)std::min(g, cap);
+}
+
+void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
+                  const int* kAt, const int* iAt, const double* At)
+{
+    sym_.analyze(m, n, kA, iA, kAt, iAt);
+    analyzed_ = true;
+    if (device_ < 0) return;
+    VBK_CUDA(cudaSetDevice(device_));
+    const int N = sym_.N, nz = sym_.nzA, lnz = sym_.lnz();
+
+    // matrix: gather forms built from each CSC operand independently
+    std::vector<int> ptr, idx;
+    std::vector<double> val;
+    csc_to_rows(m, n, kA, iA, A, ptr, idx, val);       // rows of A  (y[m] = A x[n])
+    gA_ptr_.upload(ptr, stream_); gA_idx_.upload(idx, stream_); gA_val_.upload(val, stream_);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+    csc_to_rows(n, m, kAt, iAt, At, ptr, idx, val);    // rows of At (y[n] = At x[m])
+    gAt_ptr_.upload(ptr, stream_); gAt_idx_.upload(idx, stream_); gAt_val_.upload(val, stream_);
+    A_val_.upload(A, nz, stream_);
+    At_val_.upload(At, nz, stream_);
+    mapA_.upload(sym_.mapA, stream_);
+    mapAt_.upload(sym_.mapAt, stream_);
+
+    iperm_.upload(sym_.iperm, stream_); perm_.upload(sym_.perm, stream_);
+    kL_.upload(sym_.kL, stream_); iL_.upload(sym_.iL, stream_);
+    parent_.upload(sym_.parent, stream_); nchild_.upload(sym_.nchild, stream_);
+    rowptr_.upload(sym_.rowptr, stream_);
+    rk_sig_.upload(sym_.rk_sig, stream_); rj_sig_.upload(sym_.rj_sig, stream_);
+    rk_asc_.upload(sym_.rk_asc, stream_); rj_asc_.upload(sym_.rj_asc, stream_);
+
+    L_.alloc(lnz); diag_.alloc(N); mark_.alloc(N); pend_.alloc(N);
+    counters_.alloc(C_COUNT); scal_.alloc(S_COUNT); bits_.alloc(S_COUNT);
+    z_.alloc(N); xk_.alloc(n); yk_.alloc(m); r_.alloc(m); s_.alloc(n);
+    h_dn_.alloc(n); h_dm_.alloc(m); h_c_.alloc(n); h_b_.alloc(m);
+
+    double scal0[S_COUNT] = {0};
+    scal0[S_EPSDIAG] = 1.0e-14;                          // _EPSDIAG, ldlt.c:31,215
+    VBK_CUDA(cudaMemcpyAsync(scal_.p, scal0, sizeof(scal0), cudaMemcpyHostToDevice, stream_));
+    VBK_CUDA(cudaMemsetAsync(bits_.p, 0, sizeof(unsigned long long) * S_COUNT, stream_));
+    VBK_CUDA(cudaMemsetAsync(counters_.p, 0, sizeof(int) * C_COUNT, stream_));
+
+    // launch geometry of the persistent dataflow kernels
+    smem_slots_ = 4096;
+    factor_smem_ = sizeof(double) * ((size_t)smem_slots_ + 3 * kFactorThreads + 2) +
+                   sizeof(int) * (2 * kFactorThreads + 4);
+    int occ = 1;
+    VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_strict, kFactorThreads, factor_smem_));
+    occ = std::max(1, std::min(occ, 4));
+    long long grid = (long long)num_sms_ * occ;
+    const long long budget = (long long)6 << 30;         // bytes of per-CTA scratch we allow
+    long long per_cta = (long long)N * 4 + (long long)sym_.maxcol * 8;
+    if (grid * per_cta > budget) grid = std::max<long long>(num_sms_ / 2, budget / per_cta);
+    grid = std::max<long long>(1, std::min<long long>(grid, N));
+    factor_grid_ = (int)grid;
+#ifdef VBK_EMU
+    factor_grid_ = std::max(1, std::min(3, N));   // several CTAs, so the dataflow waits are exercised
+#endif
+    slotmap_.alloc((size_t)factor_grid_ * N);
+    gtemp_.alloc((size_t)factor_grid_ * std::max(sym_.maxcol, 1));
+    solve_grid_ = (int)std::max<long long>(1, std::min<long long>((long long)num_sms_ * 8, ((long long)N + 3) / 4));
+#ifdef VBK_EMU
+    solve_grid_ = std::min(solve_grid_, 3);
+#endif
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Kkt::read_scalars()
+{
+    bits_.download(pin_bits_, S_COUNT, stream_);
+    scal_.download(pin_scal_, S_COUNT, stream_);
+    counters_.download(pin_cnt_, C_COUNT, stream_);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+}
+
+double Kkt::epsdiag() { require_device("epsdiag"); read_scalars(); return pin_scal_[S_EPSDIAG]; }
+int Kkt::ndep() { require_device("ndep"); read_scalars(); return pin_cnt_[C_NDEP]; }
+
+void Kkt::download_factor(double* L, double* diag, int* mark)
+{
+    require_device("download_factor");
+    if (L) L_.download(L, sym_.lnz(), stream_);
+    if (diag) diag_.download(diag, sym_.N, stream_);
+    if (mark) mark_.download(mark, sym_.N, stream_);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ------------------------------------------------------------------------------------------------
+void Kkt::factor_dev(const double* d_dn, const double* d_dm)
+{
+    require_device("factor");
+    VBK_CUDA(cudaSetDevice(device_));
+    const int N = sym_.N, n = sym_.n, m = sym_.m, nz = sym_.nzA, lnz = sym_.lnz();
+    stats.factor_calls++;
+
+    // K1 assemble (inv_num, ldlt.c:235-269,280)
+    VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_MAXDIAG, 2);      // MAXDIAG, MINDIAG
+    VBK_LAUNCH(k_set_diag, vec_grid(N), kVecThreads, 0, stream_, n, m, iperm_.p, d_dn, d_dm,
+               scal_.p, diag_.p, mark_.p, bits_.p);
+    VBK_CUDA(cudaMemsetAsync(L_.p, 0, sizeof(double) * (size_t)lnz, stream_));
+    VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapA_.p, A_val_.p, L_.p);
+    VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapAt_.p, At_val_.p, L_.p);
+    VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, 0, pend_.p, counters_.p, 1);
+
+    // K2/K4 numeric LDL^T
+    FactorArgs fa;
+    fa.N = N; fa.n_ld = n; fa.maxcol = std::max(sym_.maxcol, 1); fa.smem_slots = smem_slots_;
+    fa.kL = kL_.p; fa.iL = iL_.p; fa.L = L_.p; fa.diag = diag_.p; fa.mark = mark_.p;
+    fa.rowptr = rowptr_.p; fa.rk = rk_sig_.p; fa.rj = rj_sig_.p;
+    fa.parent = parent_.p; fa.perm = perm_.p;
+    fa.pend = pend_.p; fa.counters = counters_.p; fa.scal_bits = bits_.p;
+    fa.epsnum = 0.0;                                       // _EPSNUM, ldlt.c:29
+    fa.slotmap = slotmap_.p; fa.gtemp = gtemp_.p;
+    VBK_LAUNCH(k_factor_strict, factor_grid_, kFactorThreads, factor_smem_, stream_, fa);
+
+    // epsdiag escalation (ldlt.c:293-306)
+    VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);
+    VBK_LAUNCH(k_update_epsdiag, 1, 32, 0, stream_, scal_.p, bits_.p);
+    VBK_CHECK_LAUNCH();
+    stats.kernel_launches += 9;
+}
+
+void Kkt::rawsolve_dev()
+{
+    require_device("rawsolve");
+    const int N = sym_.N;
+    stats.rawsolve_calls++;
+    SolveArgs sa;
+    sa.N = N; sa.m_ld = sym_.m;
+    sa.kL = kL_.p; sa.iL = iL_.p; sa.L = L_.p; sa.diag = diag_.p; sa.mark = mark_.p;
+    sa.rowptr = rowptr_.p; sa.rk = rk_asc_.p; sa.rj = rj_asc_.p;
+    sa.parent = parent_.p; sa.z = z_.p; sa.pend = pend_.p; sa.counters = counters_.p;
+    sa.scal_bits = bits_.p; sa.epssol = 1.0e-6;            // _EPSSOL, ldlt.c:28
+
+    // eps = epssol*maxv(z,m) is only used when the factorisation met dependent pivots (ldlt.c:446)
+    VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_ZMAX, 1);
+    VBK_LAUNCH(k_absmax, vec_grid(sym_.m), kVecThreads, 0, stream_, sym_.m, z_.p, bits_.p + S_ZMAX);
+    VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, 0, pend_.p, counters_.p, 2);
+    VBK_LAUNCH(k_fwd_strict, solve_grid_, kSolveThreads, 0, stream_, sa);
+    VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
+    VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, (const int*)nullptr, 1, pend_.p, counters_.p, 0);
+    VBK_LAUNCH(k_bwd_strict, solve_grid_, kSolveThreads, 0, stream_, sa);
+    VBK_CHECK_LAUNCH();
+    stats.kernel_launches += 7;
+}
+
+void Kkt::spmv_A(const double* d_x, double* d_y)
+{
+    require_device("spmv_A");
+    VBK_LAUNCH(k_spmv_rows, vec_grid(sym_.m), kVecThreads, 0, stream_, sym_.m, gA_ptr_.p, gA_idx_.p, gA_val_.p, d_x, d_y);
+    stats.kernel_launches++;
+}
+void Kkt::spmv_At(const double* d_x, double* d_y)
+{
+    require_device("spmv_At");
+    VBK_LAUNCH(k_spmv_rows, vec_grid(sym_.n), kVecThreads, 0, stream_, sym_.n, gAt_ptr_.p, gAt_idx_.p, gAt_val_.p, d_x, d_y);
+    stats.kernel_launches++;
+}
+
+int Kkt::solve_dev(const double* d_Dn, const double* d_Dm, double* d_c, double* d_b)
+{
+    require_device("solve");
+    VBK_CUDA(cudaSetDevice(device_));
+    const int n = sym_.n, m = sym_.m, N = sym_.N;
+    stats.solve_calls++;
+
+    VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_MAXBC_B, 2);
+    VBK_LAUNCH(k_absmax, vec_grid(m), kVecThreads, 0, stream_, m, d_b, bits_.p + S_MAXBC_B);
+    VBK_LAUNCH(k_absmax, vec_grid(n), kVecThreads, 0, stream_, n, d_c, bits_.p + S_MAXBC_C);
+    stats.kernel_launches += 3;
+
+    int pass = 0, consistent = 1;
+    double maxrs = HUGE_VAL, oldmaxrs = HUGE_VAL, maxbc = 1.0;
+    do {
+        if (pass == 0) VBK_LAUNCH(k_permute_in, vec_grid(N), kVecThreads, 0, stream_, n, m, iperm_.p, d_c, d_b, z_.p);
+        else           VBK_LAUNCH(k_permute_in, vec_grid(N), kVecThreads, 0, stream_, n, m, iperm_.p, s_.p, r_.p, z_.p);
+        rawsolve_dev();
+        VBK_LAUNCH(k_permute_out, vec_grid(N), kVecThreads, 0, stream_, n, m, pass == 0 ? 0 : 1, iperm_.p, z_.p, xk_.p, yk_.p);
+        VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_MAXR, 2);
+        // r = b - (A x_k + Dm y_k) ; s = c - (At y_k - Dn x_k)      (ldlt.c:389-398)
+        VBK_LAUNCH(k_residual, vec_grid(m), kVecThreads, 0, stream_, m, 1, gA_ptr_.p, gA_idx_.p, gA_val_.p,
+                   xk_.p, d_Dm, yk_.p, d_b, r_.p, bits_.p + S_MAXR);
+        VBK_LAUNCH(k_residual, vec_grid(n), kVecThreads, 0, stream_, n, 0, gAt_ptr_.p, gAt_idx_.p, gAt_val_.p,
+                   yk_.p, d_Dn, xk_.p, d_c, s_.p, bits_.p + S_MAXS);
+        stats.kernel_launches += 5;
+        read_scalars();
+        consistent = pin_cnt_[C_CONSISTENT];
+        if (pass == 0) {
+            double mb, mc;
+            std::memcpy(&mb, &pin_bits_[S_MAXBC_B], 8);
+            std::memcpy(&mc, &pin_bits_[S_MAXBC_C], 8);
+            maxbc = (mb > mc ? mb : mc) + 1;                                   // ldlt.c:367
+        }
+        double mr, ms;
+        std::memcpy(&mr, &pin_bits_[S_MAXR], 8);
+        std::memcpy(&ms, &pin_bits_[S_MAXS], 8);
+        oldmaxrs = maxrs;
+        maxrs = (mr > ms ? mr : ms);                                            // ldlt.c:401
+        pass++;
+        if (debug_) std::fprintf(stderr, "vbk solve: pass %d maxr %.17g maxs %.17g maxbc %.17g consistent %d\n",
+                                 pass, mr, ms, maxbc, consistent);
+    } while (maxrs > 1.0e-10 * maxbc && maxrs < oldmaxrs / 2);                  // ldlt.c:411
+
+    if (maxrs > oldmaxrs && pass > 1) {                                         // ldlt.c:413-416
+        VBK_LAUNCH(k_permute_out, vec_grid(N), kVecThreads, 0, stream_, n, m, 2, iperm_.p, z_.p, xk_.p, yk_.p);
+        stats.kernel_launches++;
+    }
+    VBK_CUDA(cudaMemcpyAsync(d_c, xk_.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, stream_));
+    VBK_CUDA(cudaMemcpyAsync(d_b, yk_.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, stream_));
+    VBK_CHECK_LAUNCH();
+    stats.last_passes = pass;
+    stats.last_consistent = consistent;
+    stats.last_ndep = pin_cnt_[C_NDEP];
+    return consistent;
+}
+
+void Kkt::factor_host(const double* dn, const double* dm)
+{
+    require_device("factor");
+    VBK_CUDA(cudaSetDevice(device_));
+    h_dn_.upload(dn, sym_.n, stream_);
+    h_dm_.upload(dm, sym_.m, stream_);
+    factor_dev(h_dn_.p, h_dm_.p);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+}
+
+int Kkt::solve_host(const double* Dn, const double* Dm, double* c, double* b)
+{
+    require_device("solve");
+    VBK_CUDA(cudaSetDevice(device_));
+    h_dn_.upload(Dn, sym_.n, stream_);
+    h_dm_.upload(Dm, sym_.m, stream_);
+    h_c_.upload(c, sym_.n, stream_);
+    h_b_.upload(b, sym_.m, stream_);
+    int consistent = solve_dev(h_dn_.p, h_dm_.p, h_c_.p, h_b_.p);
+    h_c_.download(c, sym_.n, stream_);
+    h_b_.download(b, sym_.m, stream_);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+    return consistent;
+}
+
+}  // namespace vbk

@@ -1,0 +1,128 @@
+// vbk_kkt.h -- the device-resident factor object ("K = [-E A; A^T D]" of one LP).
+//
+// Replaces the file-scope statics of the reference's LU plugin (src/ipo/ldlt.c:108-120) by a handle:
+// symbolic analysis once on the host (vbk_symbolic), everything numeric on the GPU.
+#pragma once
+#include "vbk_device.h"
+#include "vbk_symbolic.h"
+
+#include <cstddef>
+#include <vector>
+
+namespace vbk {
+
+enum Mode { kStrict = 0, kFast = 1 };
+
+// owning device array
+template <class T>
+struct DevArray {
+    T* p = nullptr;
+    size_t n = 0;
+    DevArray() = default;
+    DevArray(const DevArray&) = delete;
+    DevArray& operator=(const DevArray&) = delete;
+    ~DevArray() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        if (count <= n && p) return;
+        release();
+        VBK_CUDA(cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T)));
+        n = count;
+    }
+    void upload(const T* h, size_t count, cudaStream_t s) {
+        alloc(count);
+        if (count) VBK_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void upload(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }
+    void download(T* h, size_t count, cudaStream_t s) const {
+        if (count) VBK_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+struct KktStats {
+    long long factor_calls = 0, solve_calls = 0, rawsolve_calls = 0;
+    long long kernel_launches = 0;
+    int last_passes = 0, last_consistent = 1, last_ndep = 0;
+};
+
+class Kkt {
+public:
+    Kkt(int device, int mode);
+    ~Kkt();
+
+    // ldlt-space arguments, as in ldltfac (ldlt.h:1-13): A is m x n in CSC, At its transpose.
+    // Host pointers; the matrix is copied to the device once (the reference keeps the pointers
+    // and assumes the matrix never changes, ldlt.c:140-160).  device < 0: host analysis only.
+    void analyze(int m, int n, const int* kA, const int* iA, const double* A,
+                 const int* kAt, const int* iAt, const double* At);
+    bool analyzed() const { return analyzed_; }
+
+    // numeric factorisation of K(dn, dm); device pointers of length n and m (inv_num, ldlt.c:164-309)
+    void factor_dev(const double* d_dn, const double* d_dm);
+    // K^{-1} rhs with iterative refinement; c (length n) and b (length m) are overwritten
+    // (solve, ldlt.c:327-425).  Returns the `consistent` flag.
+    int solve_dev(const double* d_Dn, const double* d_Dm, double* d_c, double* d_b);
+    // one forward/diagonal/backward sweep on the permuted vector in zbuf() (rawsolve, ldlt.c:433-505)
+    void rawsolve_dev();
+
+    // host-pointer wrappers (the B1 seam): H2D, device work, D2H
+    void factor_host(const double* dn, const double* dm);
+    int solve_host(const double* Dn, const double* Dm, double* c, double* b);
+
+    // y[m] = A x[n]  /  y[n] = At x[m]  with the reference's summation order (smx, linalg.c:62-70)
+    void spmv_A(const double* d_x, double* d_y);
+    void spmv_At(const double* d_x, double* d_y);
+
+    // introspection for tests / bench
+    const Symbolic& sym() const { return sym_; }
+    void download_factor(double* L, double* diag, int* mark);
+    double epsdiag();
+    int ndep();
+    double* zbuf() { return z_.p; }
+    cudaStream_t stream() const { return stream_; }
+    int device() const { return device_; }
+    int mode() const { return mode_; }
+    KktStats stats;
+
+    int num_sms() const { return num_sms_; }
+    int vec_grid(long long n) const;
+
+private:
+    void require_device(const char* what) const;
+    void read_scalars();   // D2H of scalar/bit/counter blocks + stream sync
+
+    int device_, mode_;
+    bool debug_ = false;   // $VBK_DEBUG: trace refinement passes on stderr
+    int num_sms_ = 1;
+    cudaStream_t stream_ = 0;
+    bool analyzed_ = false;
+    Symbolic sym_;
+
+    // matrix, row-wise gather form (built on the host by stable counting sort)
+    DevArray<int> gA_ptr_, gA_idx_, gAt_ptr_, gAt_idx_;
+    DevArray<double> gA_val_, gAt_val_;
+    // raw CSC values + scatter maps for the assemble kernel
+    DevArray<double> A_val_, At_val_;
+    DevArray<int> mapA_, mapAt_;
+    // symbolic
+    DevArray<int> iperm_, perm_, kL_, iL_, parent_, nchild_, rowptr_, rk_sig_, rj_sig_, rk_asc_, rj_asc_;
+    // numeric
+    DevArray<double> L_, diag_;
+    DevArray<int> mark_, pend_, counters_, slotmap_;
+    DevArray<double> gtemp_, scal_;
+    DevArray<unsigned long long> bits_;
+    // solve work vectors
+    DevArray<double> z_, xk_, yk_, r_, s_;
+    // host-seam staging
+    DevArray<double> h_dn_, h_dm_, h_c_, h_b_;
+    // pinned readback
+    unsigned long long* pin_bits_ = nullptr;
+    double* pin_scal_ = nullptr;
+    int* pin_cnt_ = nullptr;
+
+    int factor_grid_ = 1, solve_grid_ = 1;
+    size_t factor_smem_ = 0;
+    int smem_slots_ = 4096;
+};
+
+}  // namespace vbk

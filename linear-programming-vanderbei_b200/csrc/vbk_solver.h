@@ -1,0 +1,25 @@
+// vbk_solver.h -- device-resident METHOD plugins (hsd / intpt), see vbk_solver.cu.
+#pragma once
+
+namespace vbk {
+
+struct SolveProfile {
+    double total_s = 0, setup_s = 0, factor_s = 0, solve_s = 0;
+    long long factor_calls = 0, solve_calls = 0, rawsolve_calls = 0, kernel_launches = 0;
+    long long refine_passes = 0;
+    int iterations = 0, N = 0;
+    long long lnz = 0;
+    double narth = 0;
+};
+
+// status: 0 optimal, 2 primal infeasible, 4 dual infeasible, 5 iteration limit (main.c:21-30)
+int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
+               const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof);
+int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
+                 const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof);
+
+// Test hook: copy the KKT-step inputs (E[m], D[n], rhs_y[m], rhs_x[n]) and outputs (sol_y, sol_x) of
+// iteration `iter` of the next solver_* call into host buffers; iter < 0 disables.
+void set_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x);
+
+}  // namespace vbk

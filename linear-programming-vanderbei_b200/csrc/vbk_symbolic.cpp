@@ -1,0 +1,315 @@
+// vbk_symbolic.cpp -- see vbk_symbolic.h.  Host-side, runs once per LP.
+#include "vbk_symbolic.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+namespace vbk {
+
+namespace {
+
+// Indexed binary min-heap, positions 1..count.  Tie behaviour must equal the reference's static
+// hfall/hrise pair (ldlt.c:1305-1349): the right child wins only when strictly smaller, and an
+// element moves only when strictly out of order.  Any other choice changes perm[].
+class KeyHeap {
+public:
+    explicit KeyHeap(int n) : key(n), where(n), at(n + 1), count(n) {}
+    std::vector<int> key;    // key per node
+    std::vector<int> where;  // heap position of node
+    std::vector<int> at;     // node at heap position (1-based)
+    int count;
+
+    int top() const { return at[1]; }
+
+    void sift_down(int pos) {
+        for (int child = 2 * pos; child <= count; child = 2 * pos) {
+            if (child < count && key[at[child + 1]] < key[at[child]]) ++child;
+            if (key[at[pos]] > key[at[child]]) { exchange(pos, child); pos = child; }
+            else break;
+        }
+    }
+    void sift_up(int pos) {
+        for (int up = pos / 2; up > 0; up = pos / 2) {
+            if (key[at[up]] > key[at[pos]]) { exchange(pos, up); pos = up; }
+            else break;
+        }
+    }
+    // ldlt.c:1125-1133: overwrite the hole with the last element, shrink, then restore order
+    // (sink if the removed key was smaller than the moved one, otherwise float).
+    void remove(int node) {
+        int pos = where[node];
+        int removed_key = key[at[pos]];
+        at[pos] = at[count];
+        where[at[pos]] = pos;
+        --count;
+        if (removed_key < key[at[pos]]) sift_down(pos);
+        else sift_up(pos);
+    }
+
+private:
+    void exchange(int a, int b) {
+        std::swap(at[a], at[b]);
+        where[at[a]] = a;
+        where[at[b]] = b;
+    }
+};
+
+}  // namespace
+
+// Tiered minimum-degree ordering with mass elimination on an explicit-fill elimination graph.
+// Follows ldlt.c:860-1262 decision for decision (method = minimum degree).
+void Symbolic::order(std::vector<std::vector<int>>& adj, std::vector<int>& tier) {
+    const int penalty = (int)(1.0 * N);  // stablty * m, ldlt.c:889
+    perm.assign(N, -1);
+    iperm.assign(N, -1);
+    kL.assign(N + 1, 0);
+    iL.clear();
+    {
+        long long half = 0;
+        for (auto& a : adj) half += (long long)a.size();
+        iL.reserve((size_t)half);  // grows as fill is discovered
+    }
+    std::vector<int> stamp(N, 0), others;
+    others.reserve(N);
+
+    KeyHeap heap(N);
+    for (int v = 0; v < N; ++v) heap.key[v] = (int)adj[v].size();
+    for (int v = 0; v < N; ++v) {
+        if ((int)adj[v].size() > dense && tier[v] == 0) tier[v] = 1;  // ldlt.c:994-999
+        heap.key[v] += tier[v] * penalty;
+    }
+    for (int v = N - 1; v >= 0; --v) {  // ldlt.c:1004-1010
+        heap.where[v] = v + 1;
+        heap.at[v + 1] = v;
+        heap.sift_down(v + 1);
+    }
+
+    int tag = 0;
+    denwin = N;
+    for (int i = 0; i < N;) {
+        const int pivot = heap.top();
+        const int d = (int)adj[pivot].size();
+        if (d >= N - 1 - i) denwin = i;  // ldlt.c:1027
+        perm[i] = pivot;
+        iperm[pivot] = i;
+
+        // neighbours indistinguishable from the pivot join its group (ldlt.c:1037-1054)
+        for (int u : adj[pivot]) iperm[u] = i;
+        others.clear();
+        int iend = i + 1;
+        for (int u : adj[pivot]) {
+            bool same = ((int)adj[u].size() == d) && tier[u] == tier[pivot];
+            if (same) {
+                for (int w : adj[u]) if (iperm[w] < i) { same = false; break; }
+            }
+            if (same) { perm[iend] = u; iperm[u] = iend; ++iend; }
+            else others.push_back(u);
+        }
+
+        // column structures of the group members (ldlt.c:1068-1088); old node ids for now
+        for (int ii = i, len = d; ii < iend; ++ii, --len) {
+            kL[ii + 1] = kL[ii] + len;
+            for (int w : adj[perm[ii]]) {
+                int row = iperm[w];
+                if (row > ii || (row == i && w != pivot)) iL.push_back(w);
+            }
+        }
+
+        // drop the eliminated nodes from the survivors' lists, keeping order (ldlt.c:1094-1120)
+        for (int u : others) {
+            auto& lst = adj[u];
+            lst.erase(std::find(lst.begin(), lst.end(), pivot));
+        }
+        if (iend > i + 1) {
+            for (int u : others) {
+                auto& lst = adj[u];
+                lst.erase(std::remove_if(lst.begin(), lst.end(), [&](int w) { return iperm[w] > i; }),
+                          lst.end());
+            }
+        }
+
+        for (int ii = i; ii < iend; ++ii) heap.remove(perm[ii]);  // ldlt.c:1122-1134
+
+        // pairwise fill among the survivors, appended at the list ends (ldlt.c:1144-1201)
+        for (size_t a = 0; a < others.size(); ++a) {
+            int u = others[a];
+            ++tag;
+            for (int w : adj[u]) stamp[w] = tag;
+            for (size_t b = a + 1; b < others.size(); ++b) {
+                int w = others[b];
+                if (stamp[w] != tag) { adj[u].push_back(w); adj[w].push_back(u); }
+            }
+        }
+
+        // re-key survivors in list order: float, then sink (ldlt.c:1206-1220)
+        for (int u : others) {
+            heap.key[u] = (int)adj[u].size() + (tier[u] != 0 ? tier[u] * penalty : 0);
+            heap.sift_up(heap.where[u]);
+            heap.sift_down(heap.where[u]);
+        }
+
+        for (int ii = i; ii < iend; ++ii) std::vector<int>().swap(adj[perm[ii]]);
+        i = iend;
+    }
+
+    for (int& r : iL) r = iperm[r];  // ldlt.c:1236
+    for (int j = 0; j < N; ++j) std::sort(iL.begin() + kL[j], iL.begin() + kL[j + 1]);  // :1238
+    iL.shrink_to_fit();
+
+    narth = 0.0;
+    for (int j = 0; j < N; ++j) { double c = kL[j + 1] - kL[j]; narth += c * c; }
+    narth = narth + 3.0 * kL[N] + N;
+}
+
+void Symbolic::analyze(int m_, int n_, const int* kA, const int* iA, const int* kAt, const int* iAt) {
+    m = m_; n = n_; N = m + n; nzA = kA[n];
+
+    // ordering priority from the two fill estimates (ldlt.c:687-717); double arithmetic in the
+    // reference's loop order because a borderline comparison could flip otherwise
+    double fraction = 1.0e0;
+    for (int j = 0; j < n; ++j) {
+        double dens = (double)(kA[j + 1] - kA[j]) / (m + 1);
+        fraction = fraction * (1.0e0 - dens * dens);
+    }
+    const double pfillin = 0.5 * m * m * (1.0e0 - fraction);
+    fraction = 1.0e0;
+    for (int i = 0; i < m; ++i) {
+        double dens = (double)(kAt[i + 1] - kAt[i]) / (n + 1);
+        fraction = fraction * (1.0e0 - dens * dens);
+    }
+    const double dfillin = 0.5 * n * n * (1.0e0 - fraction);
+    pdf = (3 * pfillin <= dfillin) ? 1 : 2;  // Q is empty, so "separable" is true
+
+    // adjacency of K in the reference's initial neighbour order (ldlt.c:727-759)
+    std::vector<std::vector<int>> adj(N);
+    for (int j = 0; j < n; ++j) {
+        adj[j].reserve(2 * (size_t)(kA[j + 1] - kA[j]));
+        for (int k = kA[j]; k < kA[j + 1]; ++k) adj[j].push_back(n + iA[k]);
+    }
+    for (int i = 0; i < m; ++i) {
+        adj[n + i].reserve(2 * (size_t)(kAt[i + 1] - kAt[i]));
+        adj[n + i].assign(iAt + kAt[i], iAt + kAt[i + 1]);
+    }
+    // tiers (ldlt.c:766-809) for bndmark=BDD_BELOW, rngmark=INFINITE: favoured side 0, other 1
+    std::vector<int> tier(N);
+    for (int j = 0; j < n; ++j) tier[j] = (pdf == 1) ? 0 : 1;
+    for (int i = 0; i < m; ++i) tier[n + i] = (pdf == 1) ? 1 : 0;
+    dense = 3;  // ldlt.c:814-846 with n1 == 0
+
+    order(adj, tier);
+    derive(kA, iA, kAt, iAt);
+}
+
+void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* iAt) {
+    const int lnz_ = kL[N];
+
+    // elimination tree: rows ascend inside a column, so the parent is the first stored row
+    parent.assign(N, -1);
+    nchild.assign(N, 0);
+    height.assign(N, 0);
+    maxcol = 0;
+    for (int j = 0; j < N; ++j) {
+        int c = kL[j + 1] - kL[j];
+        maxcol = std::max(maxcol, c);
+        if (c > 0) { parent[j] = iL[kL[j]]; nchild[parent[j]]++; }
+    }
+    nlevels = 0;
+    for (int j = 0; j < N; ++j) {  // children precede parents
+        if (parent[j] >= 0) height[parent[j]] = std::max(height[parent[j]], height[j] + 1);
+        nlevels = std::max(nlevels, height[j] + 1);
+    }
+    lvlptr.assign(nlevels + 1, 0);
+    for (int j = 0; j < N; ++j) lvlptr[height[j] + 1]++;
+    for (int l = 0; l < nlevels; ++l) lvlptr[l + 1] += lvlptr[l];
+    lvlcol.assign(N, 0);
+    {
+        std::vector<int> fill(lvlptr.begin(), lvlptr.end() - 1);
+        for (int j = 0; j < N; ++j) lvlcol[fill[height[j]]++] = j;
+    }
+
+    // row lists of L
+    rowptr.assign(N + 1, 0);
+    for (int k = 0; k < lnz_; ++k) rowptr[iL[k] + 1]++;
+    for (int r = 0; r < N; ++r) rowptr[r + 1] += rowptr[r];
+    rk_asc.assign(lnz_, 0); rj_asc.assign(lnz_, 0);
+    rk_sig.assign(lnz_, 0); rj_sig.assign(lnz_, 0);
+    {
+        std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
+        for (int j = 0; j < N; ++j)
+            for (int k = kL[j]; k < kL[j + 1]; ++k) {
+                int dst = fill[iL[k]]++;
+                rk_asc[dst] = k;
+                rj_asc[dst] = j;
+            }
+    }
+    {
+        // Integer skeleton of lltnum's first/link bookkeeping (ldlt.c:550-552,568-580,616-620):
+        // the order in which row r meets its columns is the order every sum of column r is
+        // accumulated in, so the numeric kernels replay exactly this list.
+        std::vector<int> cursor(N, 0), chain(N, -1);
+        for (int r = 0; r < N; ++r) {
+            int dst = rowptr[r];
+            for (int j = chain[r], nextj; j != -1; j = nextj) {
+                nextj = chain[j];
+                int k = cursor[j];
+                rk_sig[dst] = k;
+                rj_sig[dst] = j;
+                ++dst;
+                if (k + 1 < kL[j + 1]) {
+                    cursor[j] = k + 1;
+                    int row = iL[k + 1];
+                    chain[j] = chain[row];
+                    chain[row] = j;
+                }
+            }
+            if (dst != rowptr[r + 1]) { std::fprintf(stderr, "vbk: row list mismatch at %d\n", r); std::abort(); }
+            if (kL[r] < kL[r + 1]) {
+                cursor[r] = kL[r];
+                int row = iL[kL[r]];
+                chain[r] = chain[row];
+                chain[row] = r;
+            }
+        }
+    }
+
+    // scatter maps (ldlt.c:243-269): K entry (row>col) lands at the L slot of that (row, col)
+    mapA.assign(nzA, -1);
+    mapAt.assign(nzA, -1);
+    {
+        std::vector<int> slot(N, -1);
+        for (int j = 0; j < n; ++j) {
+            int col = iperm[j];
+            for (int k = kL[col]; k < kL[col + 1]; ++k) slot[iL[k]] = k;
+            for (int k = kA[j]; k < kA[j + 1]; ++k) {
+                int row = iperm[n + iA[k]];
+                if (row > col) mapA[k] = slot[row];
+            }
+        }
+        for (int i = 0; i < m; ++i) {
+            int col = iperm[n + i];
+            for (int k = kL[col]; k < kL[col + 1]; ++k) slot[iL[k]] = k;
+            for (int k = kAt[i]; k < kAt[i + 1]; ++k) {
+                int row = iperm[iAt[k]];
+                if (row > col) mapAt[k] = slot[row];
+            }
+        }
+    }
+
+    // fundamental supernodes: column j+1 continues j's supernode when j+1 is j's only-child parent
+    // and struct(j+1) = struct(j) \ {j+1}
+    sn_ptr.clear();
+    sn_of.assign(N, 0);
+    for (int j = 0; j < N; ++j) {
+        bool cont = false;
+        if (j > 0) {
+            int cprev = kL[j] - kL[j - 1], ccur = kL[j + 1] - kL[j];
+            cont = parent[j - 1] == j && nchild[j] == 1 && ccur == cprev - 1;
+        }
+        if (!cont) sn_ptr.push_back(j);
+        sn_of[j] = (int)sn_ptr.size() - 1;
+    }
+    sn_ptr.push_back(N);
+}
+
+}  // namespace vbk

@@ -172,3 +172,120 @@ def iteration_lines(log: str):
         if seen and line[:9].strip().isdigit():
             out.append(line.rstrip())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle restatement helpers (oracle/libkkt_oracle.so) -- tests only
+# ------------------------------------------------------------------------------------------------
+def declare_oracle(lib):
+    lib.kko_dotprod.restype = C.c_double
+    lib.kko_dotprod.argtypes = [c_double_p, c_double_p, C.c_int]
+    lib.kko_maxv.restype = C.c_double
+    lib.kko_maxv.argtypes = [c_double_p, C.c_int]
+    lib.kko_smx.argtypes = [C.c_int, C.c_int, c_double_p, c_int_p, c_int_p, c_double_p, c_double_p]
+    lib.kko_atnum.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, c_int_p, c_int_p, c_double_p]
+    lib.kko_create.restype = C.c_void_p
+    lib.kko_destroy.argtypes = [C.c_void_p]
+    lib.kko_ldltfac.argtypes = [C.c_void_p, C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p,
+                                c_double_p, c_int_p, c_int_p, c_double_p]
+    lib.kko_forwardbackward.argtypes = [C.c_void_p] + [c_double_p] * 4
+    lib.kko_forwardbackward.restype = C.c_int
+    lib.kko_rawsolve.argtypes = [C.c_void_p, c_double_p]
+    lib.kko_rawsolve.restype = C.c_int
+    for name, rt in [("dim", C.c_int), ("denwin", C.c_int), ("pdf", C.c_int), ("ndep", C.c_int),
+                     ("epsdiag", C.c_double), ("last_passes", C.c_int), ("perm", c_int_p),
+                     ("iperm", c_int_p), ("kAAt", c_int_p), ("iAAt", c_int_p), ("AAt", c_double_p),
+                     ("diag", c_double_p), ("mark", c_int_p)]:
+        fn = getattr(lib, "kko_" + name)
+        fn.restype = rt
+        fn.argtypes = [C.c_void_p]
+    lib.kko_capture.argtypes = [C.c_int] + [c_double_p] * 6
+    lib.kko_last_timing.argtypes = [c_double_p, c_double_p, c_int_p, c_int_p, c_int_p]
+    return lib
+
+
+class OracleFactor:
+    """Handle on the oracle's factor object, ldlt-space arguments (mirrors vbkkt.KKT)."""
+
+    def __init__(self, lib, m, n, kA, iA, A, kAt, iAt, At):
+        self.lib, self.m, self.n = lib, m, n
+        self._keep = [np.ascontiguousarray(v) for v in (kA, iA, A, kAt, iAt, At)]
+        self.h = lib.kko_create()
+
+    def factor(self, dn, dm):
+        kA, iA, A, kAt, iAt, At = self._keep
+        dn = np.ascontiguousarray(dn, dtype=np.float64)
+        dm = np.ascontiguousarray(dm, dtype=np.float64)
+        self.lib.kko_ldltfac(self.h, self.m, self.n, ptr_i(kA), ptr_i(iA), ptr_d(A), ptr_d(dn), ptr_d(dm),
+                             ptr_i(kAt), ptr_i(iAt), ptr_d(At))
+
+    def solve(self, Dn, Dm, dx, dy):
+        Dn = np.ascontiguousarray(Dn, dtype=np.float64)
+        Dm = np.ascontiguousarray(Dm, dtype=np.float64)
+        dx, dy = np.array(dx, dtype=np.float64), np.array(dy, dtype=np.float64)
+        ok = self.lib.kko_forwardbackward(self.h, ptr_d(Dn), ptr_d(Dm), ptr_d(dx), ptr_d(dy))
+        return dx, dy, int(ok)
+
+    def rawsolve(self, z):
+        z = np.array(z, dtype=np.float64)
+        self.lib.kko_rawsolve(self.h, ptr_d(z))
+        return z
+
+    @property
+    def dim(self): return self.m + self.n
+    @property
+    def lnz(self): return int(self._arr(self.lib.kko_kAAt, self.dim + 1)[self.dim])
+    def _arr(self, fn, count):
+        return np.ctypeslib.as_array(fn(self.h), (max(count, 1),))[:count].copy()
+    @property
+    def perm(self): return self._arr(self.lib.kko_perm, self.dim)
+    @property
+    def kAAt(self): return self._arr(self.lib.kko_kAAt, self.dim + 1)
+    @property
+    def iAAt(self): return self._arr(self.lib.kko_iAAt, self.lnz)
+    @property
+    def L(self): return self._arr(self.lib.kko_AAt, self.lnz)
+    @property
+    def diag(self): return self._arr(self.lib.kko_diag, self.dim)
+    @property
+    def mark(self): return self._arr(self.lib.kko_mark, self.dim)
+    @property
+    def ndep(self): return int(self.lib.kko_ndep(self.h))
+    @property
+    def passes(self): return int(self.lib.kko_last_passes(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.kko_destroy(self.h)
+            self.h = None
+
+
+def capture_step(oracle, lp: LPData, method: str, it: int):
+    """Run the oracle METHOD and return (E, D, rhs_y, rhs_x, sol_y, sol_x) of iteration `it`."""
+    m, n = lp.m, lp.n
+    bufs = [np.zeros(m), np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(m), np.zeros(n)]
+    oracle.kko_capture(it, *[ptr_d(v) for v in bufs])
+    call_solver(getattr(oracle, "kko_solver_" + method), lp)
+    oracle.kko_capture(-1, None, None, None, None, None, None)
+    return bufs
+
+
+def solve_via(vbkkt, lib, lp: LPData, method: str, mode=0, profile=False):
+    """Product METHOD plugin on a fixture; returns (status, log, x, y, profile)."""
+    with capture_stdout() as cap:
+        st, x, y, prof = vbkkt.solve_lp(method, lp.m, lp.n, lp.nz, lp.iA, lp.kA, lp.A, lp.b, lp.c, lp.f,
+                                        mode=mode, profile=profile, lib=lib)
+    return st, cap.text, x, y, prof
+
+
+def kkt_for(vbkkt, lib, lp: LPData, device=0, mode=0):
+    """Factor object for a solver-space LP with the argument swap of hsd.c:218."""
+    kAt, iAt, At = transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    k = vbkkt.KKT(device=device, mode=mode, lib=lib)
+    k.analyze(lp.n, lp.m, kAt, iAt, At, lp.kA, lp.iA, lp.A)
+    return k
+
+
+def oracle_factor_for(oracle, lp: LPData):
+    kAt, iAt, At = transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    return OracleFactor(oracle, lp.n, lp.m, kAt, iAt, At, lp.kA, lp.iA, lp.A)

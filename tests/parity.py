@@ -1,0 +1,115 @@
+"""Parity checks shared by tests/test_emu.py (host emulation of the kernels, tiny inputs, CPU) and
+tests/test_gpu.py (the real thing through the C ABI on a B200).  `lib` is the library under test,
+`oracle` the plain-C restatement (checker)."""
+import numpy as np
+
+import harness as H
+
+
+def check_linalg(vbkkt, lib, oracle, sizes, seed=1):
+    rng = np.random.default_rng(seed)
+    for n in sizes:
+        x = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8, n)
+        y = rng.standard_normal(n)
+        # bit-exact: strict mode replays the reference's left-to-right sum (linalg.c:22)
+        assert vbkkt.dotprod(x, y, lib=lib) == oracle.kko_dotprod(H.ptr_d(x), H.ptr_d(y), n), n
+        assert vbkkt.maxv(x, lib=lib) == oracle.kko_maxv(H.ptr_d(x), n), n
+    z = np.array([0.0, -0.0, 0.0])
+    assert vbkkt.maxv(z, lib=lib) == 0.0
+
+
+def check_transpose_and_smx(vbkkt, lib, oracle, lp, seed=2):
+    rng = np.random.default_rng(seed)
+    kat, iat, at = vbkkt.atnum(lp.m, lp.n, lp.kA, lp.iA, lp.A, lib=lib)
+    k2, i2, a2 = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    assert np.array_equal(kat, k2) and np.array_equal(iat, i2) and np.array_equal(at, a2)
+    x = rng.standard_normal(lp.n)
+    y = vbkkt.smx(lp.m, lp.n, lp.A, lp.kA, lp.iA, x, lib=lib)
+    y2 = np.zeros(lp.m)
+    oracle.kko_smx(lp.m, lp.n, H.ptr_d(lp.A), H.ptr_i(lp.kA), H.ptr_i(lp.iA), H.ptr_d(x), H.ptr_d(y2))
+    assert np.array_equal(y, y2)
+    # transpose of the transpose is the original (size-independent property)
+    kb, ib, ab = vbkkt.atnum(lp.n, lp.m, kat, iat, at, lib=lib)
+    assert np.array_equal(kb, lp.kA[: lp.n + 1]) and np.array_equal(ab, lp.A[: lp.nz])
+
+
+def check_ragged_transpose(vbkkt, lib):
+    # empty column, empty row, a dense row
+    kA = np.array([0, 2, 2, 3, 5], dtype=np.int32)
+    iA = np.array([0, 3, 1, 0, 3], dtype=np.int32)
+    A = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    kat, iat, at = vbkkt.atnum(5, 4, kA, iA, A, lib=lib)
+    k2, i2, a2 = H.transpose_csc(5, 4, kA, iA, A)
+    assert np.array_equal(kat, k2) and np.array_equal(iat, i2) and np.array_equal(at, a2)
+    y = vbkkt.smx(5, 4, A, kA, iA, np.array([1.0, 10.0, 100.0, 1000.0]), lib=lib)
+    assert np.array_equal(y, np.array([4001.0, 300.0, 0.0, 5002.0, 0.0]))
+
+
+def check_kkt_step(vbkkt, lib, oracle, lp, method, it, refine_rhs=True):
+    """One KKT step on inputs captured from iteration `it` of the oracle's run: the numeric factor
+    (L, diag, mark, ndep) and the refined solution must be BIT-EQUAL to the oracle's."""
+    E, D, ry, rx, sy, sx = H.capture_step(oracle, lp, method, it)
+    F = H.oracle_factor_for(oracle, lp)
+    K = H.kkt_for(vbkkt, lib, lp)
+    try:
+        F.factor(E, D)
+        K.factor(E, D)
+        L, d, mk = K.get_factor()
+        assert np.array_equal(mk, F.mark)
+        assert np.array_equal(d, F.diag)
+        assert np.array_equal(L, F.L)
+        assert K.ndep == F.ndep
+        oy, ox, _ = F.solve(E, D, ry, rx)
+        gy, gx, _ = K.solve(E, D, ry, rx)
+        assert K.last_passes == F.passes
+        assert np.array_equal(gy, oy) and np.array_equal(gx, ox)
+        z = np.random.default_rng(it).standard_normal(lp.m + lp.n)
+        assert np.array_equal(K.rawsolve(z), F.rawsolve(z))
+        # a second factorisation on the same handles: state carried across calls (epsdiag
+        # escalation ldlt.c:293-306, mark reset ldlt.c:280) must stay in lock step
+        F.factor(E * 0.5, D * 2.0)
+        K.factor(E * 0.5, D * 2.0)
+        L, d, mk = K.get_factor()
+        assert np.array_equal(mk, F.mark) and np.array_equal(d, F.diag) and np.array_equal(L, F.L)
+        assert K.epsdiag == float(oracle.kko_epsdiag(F.h))
+        return dict(ndep=F.ndep, passes=F.passes, lnz=K.lnz)
+    finally:
+        F.close()
+        K.close()
+
+
+def check_full_solve(vbkkt, lib, lp, method, want_bits=True):
+    """The device-resident METHOD plugin against the golden fixture: same status, byte-identical
+    iteration log (the reference's golden log for hsd), bit-equal x and y."""
+    st, log, x, y, _ = H.solve_via(vbkkt, lib, lp, method)
+    assert st == int(lp.extra[method + "_status"])
+    exp = str(lp.extra[method + "_log"])
+    if log != exp:
+        a, b = log.splitlines(), exp.splitlines()
+        for i, (u, v) in enumerate(zip(a, b)):
+            assert u == v, f"{lp.name} {method}: first differing log line {i}:\n got {u!r}\n exp {v!r}"
+        assert len(a) == len(b), f"{lp.name} {method}: {len(a)} lines, expected {len(b)}"
+    if want_bits:
+        assert np.array_equal(x, lp.extra[method + "_x"])
+        assert np.array_equal(y, lp.extra[method + "_y"])
+    return st
+
+
+def north_star_tolerances(lp, method, x, y, status, log):
+    """The tolerance form of parity (BASELINE.json north_star): objective 1e-8 relative,
+    infeasibilities 1e-7, iteration count +-1, same status."""
+    xr, yr = lp.extra[method + "_x"], lp.extra[method + "_y"]
+    assert status == int(lp.extra[method + "_status"])
+    obj, obj_r = float(lp.c @ x), float(lp.c @ xr)
+    assert abs(obj - obj_r) <= 1e-8 * max(1.0, abs(obj_r))
+    dobj, dobj_r = float(lp.b @ y), float(lp.b @ yr)
+    assert abs(dobj - dobj_r) <= 1e-8 * max(1.0, abs(dobj_r))
+    n_it = len(H.iteration_lines(log))
+    n_ref = len(H.iteration_lines(str(lp.extra[method + "_log"])))
+    assert abs(n_it - n_ref) <= 1
+    import scipy.sparse as sp
+    A = sp.csc_matrix((lp.A, lp.iA, lp.kA), shape=(lp.m, lp.n))
+    pinf = np.linalg.norm(np.maximum(A @ x - lp.b, 0.0)), np.linalg.norm(np.maximum(A @ xr - lp.b, 0.0))
+    dinf = np.linalg.norm(np.maximum(lp.c - A.T @ y, 0.0)), np.linalg.norm(np.maximum(lp.c - A.T @ yr, 0.0))
+    assert abs(pinf[0] - pinf[1]) <= 1e-7 * max(1.0, np.linalg.norm(lp.b))
+    assert abs(dinf[0] - dinf[1]) <= 1e-7 * max(1.0, np.linalg.norm(lp.c))

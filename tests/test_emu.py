@@ -1,0 +1,44 @@
+"""CPU tests of the KERNEL LOGIC: the product's .cu sources compiled as C++ on the host thread
+emulator (tests/emu/cuda_emu.h; every CUDA thread an OS thread) and checked bit-for-bit against the
+oracle on tiny inputs.  This is test infrastructure, not a fallback -- libvbkkt.so never contains
+it.  The real-GPU versions of the same checks are in tests/test_gpu.py."""
+import pytest
+
+import harness as H
+import parity as P
+
+
+def test_emu_build_is_labelled(emu_lib):
+    assert b"TEST build" in emu_lib.vbk_version()
+
+
+def test_emu_linalg(vbkkt, emu_lib, oracle_lib):
+    P.check_linalg(vbkkt, emu_lib, oracle_lib, sizes=(0, 1, 31, 33, 67, 2047, 2049, 4500))
+
+
+def test_emu_transpose_and_smx(vbkkt, emu_lib, oracle_lib):
+    P.check_transpose_and_smx(vbkkt, emu_lib, oracle_lib, H.load_fixture("afiro"))
+    P.check_ragged_transpose(vbkkt, emu_lib)
+
+
+@pytest.mark.parametrize("method,it", [("hsd", 3), ("hsd", 26), ("intpt", 14)])
+def test_emu_kkt_step_bit_exact(vbkkt, emu_lib, oracle_lib, method, it):
+    """hsd iteration 26 has exact-zero pivots (ndep>0, ldlt.c:600-614); intpt iteration 14 needs a
+    second refinement pass (ldlt.c:411)."""
+    info = P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("afiro"), method, it)
+    if (method, it) == ("hsd", 26):
+        assert info["ndep"] > 0
+    if (method, it) == ("intpt", 14):
+        assert info["passes"] == 2
+
+
+def test_emu_kkt_step_second_problem(vbkkt, emu_lib, oracle_lib):
+    P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("sc50b"), "hsd", 10)
+
+
+def test_emu_full_solve_intpt_afiro(vbkkt, emu_lib):
+    """BASELINE.json config 1 (intpt on afiro) end to end through the emulated kernels:
+    25 log lines, status 0, byte-identical log, bit-equal x and y."""
+    lp = H.load_fixture("afiro")
+    assert P.check_full_solve(vbkkt, emu_lib, lp, "intpt") == 0
+    assert len(H.iteration_lines(str(lp.extra["intpt_log"]))) == 25

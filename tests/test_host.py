@@ -1,0 +1,73 @@
+"""CPU tests of the product's host side: C-ABI surface, symbolic analysis (bit-exact against the
+reference's perm/kAAt/iAAt for every fixture), derived structures, loud failure without a GPU."""
+import ctypes as C
+import hashlib
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import harness as H
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    header = (H.ROOT / "include" / "vbkkt.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", header))
+    names -= {"defined", "C"}
+    decl = {n for n in names if re.search(r"\b(void|int|double|long|char|vbk_kkt)\b[\s\*]+" + n + r"\s*\(", header)}
+    assert {"ldltfac", "forwardbackward", "smx", "atnum", "dotprod", "maxv", "inv_clo",
+            "vbk_solver_hsd", "vbk_solver_intpt", "vbk_kkt_create", "vbk_solve_lp"} <= decl
+    for n in sorted(decl):
+        assert hasattr(product_lib, n), f"libvbkkt.so does not export {n}"
+
+
+def test_solver_shims_export_solver(product_lib, vbkkt):
+    for meth in ("hsd", "intpt"):
+        lib = C.CDLL(str(vbkkt.PKG_DIR / f"libvbkkt_{meth}.so"))
+        assert hasattr(lib, "solver")
+
+
+def test_product_does_not_link_oracle(vbkkt):
+    out = subprocess.run(["ldd", str(vbkkt.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libref" not in out and "emu" not in out
+    syms = subprocess.run(["nm", "-D", str(vbkkt.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "kko_" not in syms
+
+
+@pytest.mark.parametrize("name", H.fixture_names())
+def test_symbolic_is_bit_exact(vbkkt, product_lib, name):
+    """perm, iperm, kAAt, iAAt, denwin, pdf of the product's host analysis == the reference's
+    (reference src/ipo/ldlt.c:638-1262), for every committed netlib fixture."""
+    lp = H.load_fixture(name)
+    k = H.kkt_for(vbkkt, product_lib, lp, device=-1)
+    assert k.dim == lp.m + lp.n
+    perm = k.perm
+    assert np.array_equal(perm, lp.extra["sym_perm"])
+    assert np.array_equal(k.iperm[perm], np.arange(k.dim))
+    assert np.array_equal(k.kAAt, lp.extra["sym_kAAt"])
+    iL = k.iAAt.astype(np.int32)
+    assert hashlib.sha256(iL.tobytes()).hexdigest() == str(lp.extra["sym_iAAt_sha256"])
+    if "sym_iAAt" in lp.extra:
+        assert np.array_equal(iL, lp.extra["sym_iAAt"])
+    assert k.denwin == int(lp.extra["sym_denwin"])
+    assert k.pdf == int(lp.extra["sym_pdf"])
+    assert k.lnz == int(lp.extra["sym_lnz"])
+    assert k.narth == float(lp.extra["sym_narth"])
+    k.close()
+
+
+def test_numeric_call_without_gpu_fails_loudly(vbkkt, product_lib):
+    """No CPU fallback: on a box without a CUDA device a numeric entry point terminates the process
+    with a message (run in a child so the test process survives)."""
+    if product_lib.vbk_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    code = ("import importlib.util,sys,numpy as np;"
+            f"spec=importlib.util.spec_from_file_location('vbkkt', r'{vbkkt.PKG_DIR}/__init__.py');"
+            "m=importlib.util.module_from_spec(spec);spec.loader.exec_module(m);"
+            "print(m.dotprod(np.ones(4),np.ones(4)))")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr and "no CPU path" in r.stderr
