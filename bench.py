@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- the KKT step (LDL^T factor + solves) of Vanderbei's hsd interior-point method on B200.
+
+One "step" = the KKT work of one hsd iteration (reference src/ipo/hsd.c:215-228) on a fixed
+mid-solve iterate of a netlib LP: 1 x ldltfac (assemble + numeric LDL^T) and 2 x forwardbackward
+(forward/diagonal/backward sweeps with iterative refinement, 2 SpMVs and 2 max-norms per pass).
+The iterate (E, D, right-hand sides) is a committed fixture produced by the pinned oracle
+(tests/golden/iterates/, see make_iterates.py), so the GPU arm, the CPU baseline and the reference
+arm all work on byte-identical inputs, and the GPU result is checked against the reference's
+solution inside the bench.
+
+Metric (BASELINE.json): LDL^T factor+solve GFLOP/s, with the reference's own work model
+(SURVEY.md 8d): F_fac = narth = sum_j c_j^2 + 3 Lnz + N (ldlt.c:1243-1248), F_rawsolve = 4 Lnz + N,
+F_smx = 2 nz.  `value`: inputs resident in HBM, device-pointer calls, CUDA events on the library's
+stream.  `e2e`: the same step through the host-buffer C ABI (what the reference's hsd.c would call:
+ldltfac / forwardbackward), pinned host arrays, H2D+D2H inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload pilot87] [--mode strict|fast]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_workload(name, it):
+    import harness as H
+    lp = H.load_fixture(name)
+    z = np.load(H.GOLDEN / "iterates" / f"{name}_it{it}.npz")
+    return lp, {k: z[k] for k in z.files}
+
+
+def work_model(sym_narth, lnz, N, nz, rawsolves, factors=1):
+    """flops of `factors` factorisations + `rawsolves` refinement passes (each 1 rawsolve + 2 smx)."""
+    f_fac = sym_narth
+    f_sol = 4.0 * lnz + N
+    f_smx = 2.0 * nz
+    return factors * f_fac + rawsolves * (f_sol + 2 * f_smx)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference / CPU arm: the compiled reference (oracle/_ref) when present, else the oracle port
+# ----------------------------------------------------------------------------------------------
+class CpuKkt:
+    def __init__(self, lp):
+        import harness as H
+        self.H, self.lp = H, lp
+        self.kAt, self.iAt, self.At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+        ref = H.load_ref("hsd")
+        if ref is not None:
+            self.kind, self.lib = "reference", ref
+            ref.ldltfac.argtypes = [C.c_int, C.c_int, H.c_int_p, H.c_int_p, H.c_double_p, H.c_double_p,
+                                    H.c_double_p, H.c_int_p, H.c_int_p, H.c_double_p, C.c_int]
+            ref.forwardbackward.argtypes = [H.c_double_p] * 4
+        else:
+            subprocess.run(["make", "-C", str(ROOT / "oracle"), "restatement"], check=True, stdout=subprocess.DEVNULL)
+            self.kind = "port"
+            self.lib = H.declare_oracle(C.CDLL(str(ROOT / "oracle" / "libkkt_oracle.so")))
+            self.F = H.oracle_factor_for(self.lib, lp)
+
+    def step(self, it):
+        """One KKT step exactly as hsd.c:218-228 issues it; returns the first solution."""
+        H, lp = self.H, self.lp
+        E, D = it["E"], it["D"]
+        fy, fx = it["rhs_y"].copy(), it["rhs_x"].copy()
+        gy, gx = -lp.b, -lp.c
+        if self.kind == "reference":
+            self.lib.ldltfac(lp.n, lp.m, H.ptr_i(self.kAt), H.ptr_i(self.iAt), H.ptr_d(self.At), H.ptr_d(E),
+                             H.ptr_d(D), H.ptr_i(lp.kA), H.ptr_i(lp.iA), H.ptr_d(lp.A), 1)
+            self.lib.forwardbackward(H.ptr_d(E), H.ptr_d(D), H.ptr_d(fy), H.ptr_d(fx))
+            self.lib.forwardbackward(H.ptr_d(E), H.ptr_d(D), H.ptr_d(gy), H.ptr_d(gx))
+        else:
+            self.F.factor(E, D)
+            fy, fx, _ = self.F.solve(E, D, fy, fx)
+            self.F.solve(E, D, gy, gx)
+        return fy, fx
+
+
+def cpu_measure(lp, it, flops_per_step, budget_s, max_steps):
+    cpu = CpuKkt(lp)
+    t0 = time.perf_counter()
+    cpu.step(it)                                   # includes the one-time symbolic phase; not timed below
+    first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cpu.step(it)
+    one = time.perf_counter() - t0
+    steps = int(max(1, min(max_steps, budget_s / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu.step(it)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": flops_per_step / dt / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": cpu.kind,
+            "sample": f"{steps} KKT steps (1 ldltfac + 2 forwardbackward) of the same workload, "
+                      f"{dt * 1e3:.2f} ms/step on 1 host core; symbolic phase ({first:.2f} s incl. first step) excluded",
+            "ms_per_step": dt * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("VBK_BENCH_WORKLOAD", "pilot87"))
+    ap.add_argument("--iterate", type=int, default=20)
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    lp, it = load_workload(a.workload, a.iterate)
+    N, nz = lp.m + lp.n, lp.nz
+    config = {"workload": f"netlib {a.workload} (solver-space m={lp.m} n={lp.n} nz={nz}, N={N}), hsd iterate "
+                          f"{a.iterate}: 1 ldltfac + 2 forwardbackward per step", "mode": a.mode,
+              "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"{world} independent LP replica(s)"}
+    metric = "LDL^T factor+solve GFLOP/s (hsd KKT step)"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import harness as H
+        vb = _load("vbkkt", ROOT / "linear-programming-vanderbei_b200" / "__init__.py")
+        sym = H.kkt_for(vb, vb.load(), lp, device=-1)           # host-only symbolic, for the flop model
+        cpu = CpuKkt(lp)
+        sol_y, _ = cpu.step(it)
+        passes = 0
+        if cpu.kind == "port":
+            passes = cpu.F.passes
+        raw = int(it.get("rawsolves", 0)) or 3
+        flops = work_model(sym.narth, sym.lnz, N, nz, raw)
+        for _ in range(a.warmup):
+            cpu.step(it)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            cpu.step(it)
+        dt = (time.perf_counter() - t0) / a.steps
+        v = flops / dt / 1e9
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": "GFLOP/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "netlib LP fixture + oracle-generated iterate", "config": config,
+            "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": 1, "kind": cpu.kind,
+                             "sample": f"{a.steps} KKT steps, {dt * 1e3:.2f} ms/step, 1 host core (the reference is single-threaded)"},
+            "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "flops_per_step": flops}))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    vb = _load("vbkkt", ROOT / "linear-programming-vanderbei_b200" / "__init__.py")
+    lib = vb.load()
+    if lib.vbk_device_count() < 1 or not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the KKT path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = vb.MODE_STRICT if a.mode == "strict" else vb.MODE_FAST
+    import harness as H
+    K = H.kkt_for(vb, lib, lp, device=local_rank, mode=mode)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(K.stream, device=dev)
+
+    def dten(v):
+        return torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+
+    E_d, D_d = dten(it["E"]), dten(it["D"])
+    ry_d, rx_d, b_d, c_d = dten(it["rhs_y"]), dten(it["rhs_x"]), dten(-lp.b), dten(-lp.c)
+    fy, fx, gy, gx = (torch.empty_like(t) for t in (ry_d, rx_d, b_d, c_d))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    passes_seen = []
+
+    def step_dev():
+        with torch.cuda.stream(stream):
+            fy.copy_(ry_d); fx.copy_(rx_d); gy.copy_(b_d); gx.copy_(c_d)
+        K.factor_dev(E_d.data_ptr(), D_d.data_ptr())
+        K.solve_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr())
+        p1 = K.last_passes
+        K.solve_dev(E_d.data_ptr(), D_d.data_ptr(), gy.data_ptr(), gx.data_ptr())
+        passes_seen.append(p1 + K.last_passes)
+
+    for _ in range(a.warmup):
+        step_dev()
+    K.sync()
+    # parity gate inside the bench: the solution of the first right-hand side equals the reference's
+    sol_y = fy.cpu().numpy()
+    ref_y = it["sol_y"]
+    err = float(np.max(np.abs(sol_y - ref_y)) / max(np.max(np.abs(ref_y)), 1e-300))
+    bit_equal = bool(np.array_equal(sol_y, ref_y))
+    if a.mode == "strict":
+        assert bit_equal, f"strict mode lost bit-parity with the reference (max rel err {err:.3e})"
+    else:
+        assert err < 1e-6, f"fast mode solution off by {err:.3e}"
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = K.launches
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    fac_ms = []
+    for s in range(a.steps):
+        flush.fill_(s & 0xFF)                       # evict L2 (126 MB) between timed steps, untimed
+        torch.cuda.synchronize()
+        ev[s][0].record(stream)
+        step_dev()
+        ev[s][1].record(stream)
+        K.sync()
+        fac_ms.append(float(lib.vbk_kkt_last_factor_kernel_ms(K.h)))
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    total_ms = float(sum(step_ms))
+    launches = K.launches - launches0
+    if dist:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / a.steps
+    raw_per_step = float(np.mean(passes_seen[-a.steps:]))
+    flops_step = work_model(K.narth, K.lnz, N, nz, raw_per_step)
+    value = world * flops_step / (ms_per_step * 1e-3) / 1e9
+
+    # e2e: host buffers (pinned) through the reference-facing C ABI: H2D + D2H inside the timed region
+    def pinned(v):
+        t = torch.empty(v.shape, dtype=torch.float64, pin_memory=True)
+        t.copy_(torch.from_numpy(np.ascontiguousarray(v)))
+        return t
+    hE, hD, hry, hrx, hb, hc = (pinned(v) for v in (it["E"], it["D"], it["rhs_y"], it["rhs_x"], -lp.b, -lp.c))
+    wy, wx, wgy, wgx = (torch.empty_like(t).pin_memory() for t in (hry, hrx, hb, hc))
+    dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+
+    def step_host():
+        wy.copy_(hry); wx.copy_(hrx); wgy.copy_(hb); wgx.copy_(hc)
+        lib.vbk_kkt_factor(K.h, dp(hE), dp(hD))
+        lib.vbk_kkt_solve(K.h, dp(hE), dp(hD), dp(wy), dp(wx))
+        lib.vbk_kkt_solve(K.h, dp(hE), dp(hD), dp(wgy), dp(wgx))
+
+    for _ in range(2):
+        step_host()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_host()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    if dist:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.summary()
+    assert np.array_equal(wy.numpy(), sol_y), "host-buffer path and device-pointer path disagree"
+    e2e = {"value": world * flops_step / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(8 * N + 2 * 16 * N), "d2h_bytes_per_step": int(2 * 8 * N)}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (numeric LDL^T): algorithmic bytes / flops per launch
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    fac_s = float(np.mean(fac_ms)) * 1e-3
+    b_fac = 12.0 * K.lnz + 8.0 * K.lnz + 2 * 12.0 * nz + 24.0 * N
+    fp64_peak = float(lib.vbk_measure_fp64_tflops(local_rank))
+    roofline = {"kernel": "k_factor_strict" if a.mode == "strict" else "factor (fast)", "bound": "hbm",
+                "achieved": b_fac / fac_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": b_fac / fac_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": fac_s * 1e3, "share_of_step": fac_s * 1e3 / ms_per_step,
+                "fp64": {"achieved_tflops": K.narth / fac_s / 1e12, "peak_tflops": fp64_peak,
+                         "frac": K.narth / fac_s / 1e12 / max(fp64_peak, 1e-9),
+                         "peak_source": "measured here (DFMA yardstick kernel, vbk_measure_fp64_tflops)"},
+                "note": "strict mode replays the reference's rounding order and is latency-bound by design (SURVEY 8d)"
+                if a.mode == "strict" else ""}
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        cpu = cpu_measure(lp, it, flops_step, a.cpu_budget, 200)
+    out = {"metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "netlib LP fixture + oracle-generated hsd iterate (tests/golden)",
+           "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "cpu_baseline": cpu, "flops_per_step": flops_step, "rawsolves_per_step": raw_per_step,
+           "parity": {"bit_equal_to_reference": bit_equal, "max_rel_err": err},
+           "symbolic": {"N": N, "lnz": K.lnz, "narth": K.narth, "levels": K.nlevels, "supernodes": K.nsupernodes}}
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

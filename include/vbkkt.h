@@ -111,6 +111,14 @@ int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const i
                  const double *A, const double *b, const double *c, double f,
                  double *x, double *y, vbk_profile *prof);
 
+/* MAX_ITER is a compile-time 200 in the reference (hsd.c:25, intpt.c:31); <=0 restores it */
+void vbk_set_iteration_limit(int itnlim);
+/* device time (ms, CUDA events on the handle's stream) of the last numeric-factor kernel */
+float vbk_kkt_last_factor_kernel_ms(vbk_kkt *h);
+/* roofline yardsticks measured on the spot: FP64 DFMA TFLOP/s and device copy GB/s */
+double vbk_measure_fp64_tflops(int device);
+double vbk_measure_hbm_gbs(int device);
+
 /* Test hook (mirrors the oracle's kko_capture): copy the KKT-step inputs E[m], D[n], rhs_y[m], rhs_x[n]
  * and outputs sol_y[m], sol_x[n] of iteration `iter` of the next solve into host buffers; iter<0 = off. */
 void vbk_capture(int iter, double *E, double *D, double *rhs_y, double *rhs_x, double *sol_y, double *sol_x);

@@ -102,6 +102,14 @@ def _declare(lib):
         fn.argtypes = [C.c_void_p]
         fn.restype = rt
     lib.vbk_kkt_get_factor.argtypes = [C.c_void_p, _dp, _dp, _ip]
+    lib.vbk_kkt_last_factor_kernel_ms.argtypes = [C.c_void_p]
+    lib.vbk_kkt_last_factor_kernel_ms.restype = C.c_float
+    lib.vbk_set_iteration_limit.argtypes = [C.c_int]
+    lib.vbk_measure_fp64_tflops.argtypes = [C.c_int]
+    lib.vbk_measure_fp64_tflops.restype = C.c_double
+    lib.vbk_measure_hbm_gbs.argtypes = [C.c_int]
+    lib.vbk_measure_hbm_gbs.restype = C.c_double
+    lib.vbk_capture.argtypes = [C.c_int] + [_dp] * 6
     return lib
 
 
@@ -266,6 +274,22 @@ class KKT:
     @property
     def stream(self):
         return self.lib.vbk_kkt_stream(self.h)
+
+
+def capture_iterate(method, m, n, nz, iA, kA, A, b, c, f, it, device=0, mode=MODE_STRICT, lib=None):
+    """Run the device-resident METHOD up to iteration `it` and return the KKT-step inputs and outputs
+    of that iteration: (E[m], D[n], rhs_y[m], rhs_x[n], sol_y[m], sol_x[n]).  Used by the bench to get a
+    realistic interior-point iterate as input for the timed KKT steps."""
+    lib = lib or load()
+    bufs = [np.zeros(m), np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(m), np.zeros(n)]
+    lib.vbk_capture(it, *[_d(v) for v in bufs])
+    lib.vbk_set_iteration_limit(it + 1)
+    try:
+        solve_lp(method, m, n, nz, iA, kA, A, b, c, f, device=device, mode=mode, lib=lib)
+    finally:
+        lib.vbk_set_iteration_limit(0)
+        lib.vbk_capture(-1, None, None, None, None, None, None)
+    return bufs
 
 
 def solve_lp(method, m, n, nz, iA, kA, A, b, c, f=0.0, device=0, mode=MODE_STRICT, profile=False, lib=None):

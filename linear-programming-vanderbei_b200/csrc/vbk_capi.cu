@@ -156,6 +156,11 @@ int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const i
     return st;
 }
 
+void vbk_set_iteration_limit(int itnlim) { set_iteration_limit(itnlim); }
+float vbk_kkt_last_factor_kernel_ms(vbk_kkt* h) { return h->impl.last_factor_kernel_ms(); }
+double vbk_measure_fp64_tflops(int device) { return measure_fp64_tflops(device); }
+double vbk_measure_hbm_gbs(int device) { return measure_hbm_gbs(device); }
+
 void vbk_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x)
 {
     set_capture(iter, E, D, rhs_y, rhs_x, sol_y, sol_x);

@@ -53,6 +53,8 @@ Kkt::Kkt(int device, int mode) : device_(device), mode_(mode)
     VBK_CUDA(cudaMallocHost((void**)&pin_bits_, sizeof(unsigned long long) * S_COUNT));
     VBK_CUDA(cudaMallocHost((void**)&pin_scal_, sizeof(double) * S_COUNT));
     VBK_CUDA(cudaMallocHost((void**)&pin_cnt_, sizeof(int) * C_COUNT));
+    VBK_CUDA(cudaEventCreate(&ev_f0_));
+    VBK_CUDA(cudaEventCreate(&ev_f1_));
 }
 
 Kkt::~Kkt()
@@ -63,6 +65,8 @@ Kkt::~Kkt()
     if (pin_bits_) cudaFreeHost(pin_bits_);
     if (pin_scal_) cudaFreeHost(pin_scal_);
     if (pin_cnt_) cudaFreeHost(pin_cnt_);
+    if (ev_f0_) cudaEventDestroy(ev_f0_);
+    if (ev_f1_) cudaEventDestroy(ev_f1_);
 #ifndef VBK_EMU
     if (stream_) cudaStreamDestroy(stream_);
 #endif
@@ -161,6 +165,15 @@ void Kkt::read_scalars()
     VBK_CUDA(cudaStreamSynchronize(stream_));
 }
 
+float Kkt::last_factor_kernel_ms()
+{
+    require_device("last_factor_kernel_ms");
+    float ms = 0.f;
+    VBK_CUDA(cudaEventSynchronize(ev_f1_));
+    VBK_CUDA(cudaEventElapsedTime(&ms, ev_f0_, ev_f1_));
+    return ms;
+}
+
 double Kkt::epsdiag() { require_device("epsdiag"); read_scalars(); return pin_scal_[S_EPSDIAG]; }
 int Kkt::ndep() { require_device("ndep"); read_scalars(); return pin_cnt_[C_NDEP]; }
 
@@ -199,7 +212,9 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
     fa.pend = pend_.p; fa.counters = counters_.p; fa.scal_bits = bits_.p;
     fa.epsnum = 0.0;                                       // _EPSNUM, ldlt.c:29
     fa.slotmap = slotmap_.p; fa.gtemp = gtemp_.p;
+    VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
     VBK_LAUNCH(k_factor_strict, factor_grid_, kFactorThreads, factor_smem_, stream_, fa);
+    VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
 
     // epsdiag escalation (ldlt.c:293-306)
     VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);

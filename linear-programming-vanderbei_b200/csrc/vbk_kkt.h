@@ -83,6 +83,8 @@ public:
     int device() const { return device_; }
     int mode() const { return mode_; }
     KktStats stats;
+    // device time of the last numeric-factor kernel (CUDA events on the handle's stream), ms
+    float last_factor_kernel_ms();
 
     int num_sms() const { return num_sms_; }
     int vec_grid(long long n) const;
@@ -121,6 +123,7 @@ private:
     int* pin_cnt_ = nullptr;
 
     int factor_grid_ = 1, solve_grid_ = 1;
+    cudaEvent_t ev_f0_ = nullptr, ev_f1_ = nullptr;
     size_t factor_smem_ = 0;
     int smem_slots_ = 4096;
 };

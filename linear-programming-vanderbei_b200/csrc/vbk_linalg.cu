@@ -4,6 +4,7 @@
 #include "vbk_linalg.h"
 #include "vbk_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -144,6 +145,76 @@ void LinalgContext::smx_host(int m, int n, const double* a, const int* ka, const
     launches++;
     vy_.download(y, m, stream_);
     VBK_CUDA(cudaStreamSynchronize(stream_));
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Roofline yardsticks.  MEASURED_PEAKS.json carries the HBM copy bandwidth and the bf16 GEMM rate;
+// the FP64 pipe rate that bounds the wide-front factor updates is measured here: eight independent
+// DFMA chains per thread (explicit fma(), so -fmad=false does not matter), every SM full.
+// ------------------------------------------------------------------------------------------------
+static __global__ void k_fp64_yardstick(int iters, double a, double b, double* __restrict__ out)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+        r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+    double s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+    if (s == 123.456) out[0] = s;   // keep the chains alive
+}
+static __global__ void k_copy_yardstick(size_t n, const double2* __restrict__ src, double2* __restrict__ dst)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+        dst[t] = src[t];
+}
+
+double measure_fp64_tflops(int device)
+{
+    VBK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VBK_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevArray<double> out; out.alloc(1);
+    cudaEvent_t e0, e1;
+    VBK_CUDA(cudaEventCreate(&e0)); VBK_CUDA(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        VBK_CUDA(cudaEventRecord(e0, 0));
+        VBK_LAUNCH(k_fp64_yardstick, grid, block, 0, 0, iters, 1.0000001, 1e-9, out.p);
+        VBK_CUDA(cudaEventRecord(e1, 0));
+        VBK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        VBK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 8.0 * (double)iters * (double)grid * (double)block;
+        if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return best;
+}
+
+double measure_hbm_gbs(int device)
+{
+    VBK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VBK_CUDA(cudaGetDeviceProperties(&prop, device));
+    const size_t n = (size_t)1 << 26;                      // 2^26 double2 = 1 GiB
+    DevArray<double> a, b; a.alloc(2 * n); b.alloc(2 * n);
+    VBK_CUDA(cudaMemset(a.p, 0, 16 * n));
+    cudaEvent_t e0, e1;
+    VBK_CUDA(cudaEventCreate(&e0)); VBK_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        VBK_CUDA(cudaEventRecord(e0, 0));
+        VBK_LAUNCH(k_copy_yardstick, prop.multiProcessorCount * 16, 512, 0, 0, n, (const double2*)a.p, (double2*)b.p);
+        VBK_CUDA(cudaEventRecord(e1, 0));
+        VBK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        VBK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms > 0) best = std::max(best, 2.0 * 16.0 * (double)n / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return best;
 }
 
 }  // namespace vbk

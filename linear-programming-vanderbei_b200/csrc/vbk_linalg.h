@@ -39,4 +39,8 @@ private:
     DevArray<int> ka_, ia_, kat_, iat_, cnt_, fill_, pos_;
 };
 
+// yardsticks for the roofline denominators that MEASURED_PEAKS.json does not carry
+double measure_fp64_tflops(int device);   // dependent-free DFMA streams on every SM
+double measure_hbm_gbs(int device);       // device-to-device copy of 1 GiB
+
 }  // namespace vbk

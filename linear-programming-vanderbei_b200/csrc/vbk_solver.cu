@@ -145,6 +145,9 @@ void show_small_problem(int m, int n, const int* kA, const int* iA, const double
 
 }  // namespace
 
+static int g_itnlim = 200;
+void set_iteration_limit(int itnlim) { g_itnlim = itnlim > 0 ? itnlim : 200; }
+
 void set_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x)
 {
     g_cap.iter = iter; g_cap.E = E; g_cap.D = D; g_cap.ry = rhs_y; g_cap.rx = rhs_x; g_cap.sy = sol_y; g_cap.sx = sol_x;
@@ -176,7 +179,7 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
     if (timed) { cudaStreamSynchronize(st); prof->setup_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); }
 
     int iter;
-    for (iter = 0; iter < 200; iter++) {
+    for (iter = 0; iter < g_itnlim; iter++) {
         double d[4];
         {
             DotJob jobs[4] = {{W.z.p, W.x.p, n}, {W.w.p, W.y.p, m}, {W.c.p, W.x.p, n}, {W.b.p, W.y.p, m}};
@@ -304,7 +307,7 @@ int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, cons
     if (timed) { cudaStreamSynchronize(st); prof->setup_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); }
 
     int iter;
-    for (iter = 0; iter < 200; iter++) {
+    for (iter = 0; iter < g_itnlim; iter++) {
         // intpt.c:139-149
         W.mul_A(W.x.p, W.rho.p);
         VBK_LAUNCH(k_pf_infeas, W.g(m), kVecThreads, 0, st, m, 0, W.b.p, W.w.p, W.rho.p);

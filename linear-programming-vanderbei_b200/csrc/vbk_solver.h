@@ -20,6 +20,10 @@ int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, cons
 
 // Test hook: copy the KKT-step inputs (E[m], D[n], rhs_y[m], rhs_x[n]) and outputs (sol_y, sol_x) of
 // iteration `iter` of the next solver_* call into host buffers; iter < 0 disables.
+// MAX_ITER of hsd.c:25 / intpt.c:31 is a compile-time 200 in the reference; tests and the bench may
+// lower it (e.g. to stop right after a captured iteration).  <= 0 restores 200.
+void set_iteration_limit(int itnlim);
+
 void set_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x);
 
 }  // namespace vbk

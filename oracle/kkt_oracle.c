@@ -617,6 +617,8 @@ void kko_last_timing(double *t_factor, double *t_solve, int *n_factor, int *n_so
     if (n_solve) *n_solve = g_n_solve;
     if (n_raw) *n_raw = g_n_rawsolve;
 }
+static int g_itnlim = 200;   /* MAX_ITER, hsd.c:25 / intpt.c:31 */
+void kko_set_itnlim(int itnlim) { g_itnlim = itnlim > 0 ? itnlim : 200; }
 static void timing_reset(void) { g_t_factor = g_t_solve = 0.0; g_n_factor = g_n_solve = g_n_rawsolve = 0; }
 
 static void show_small_problem(int m, int n, const int *kA, const int *iA, const double *A,
@@ -669,7 +671,7 @@ int kko_solver_hsd(int m, int n, int nz, int *iA, int *kA, double *A, double *b,
 "- - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - \n");
     fflush(stdout);
 
-    for (iter = 0; iter < 200; iter++) {
+    for (iter = 0; iter < g_itnlim; iter++) {
         mu = (kko_dotprod(z, x, n) + kko_dotprod(w, y, m) + phi * psi) / (n + m + 1);
         delta = (iter % 2 == 0) ? 0.0 : 1.0;
         primal_obj = kko_dotprod(c, x, n);
@@ -795,7 +797,7 @@ int kko_solver_intpt(int m, int n, int nz, int *iA, int *kA, double *A, double *
 "- - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - \n");
     fflush(stdout);
 
-    for (iter = 0; iter < 200; iter++) {
+    for (iter = 0; iter < g_itnlim; iter++) {
         kko_smx(m, n, A, kA, iA, x, rho);
         for (i = 0; i < m; i++) rho[i] = b[i] - rho[i] - w[i];
         normr = sqrt(kko_dotprod(rho, rho, m));

@@ -68,6 +68,8 @@ int kko_solver_intpt(int m, int n, int nz, int *iA, int *kA, double *A, double *
  * into caller buffers; pass iter<0 to disable.  Used to make per-call parity vectors. */
 void kko_capture(int iter, double *E, double *D, double *rhs_y, double *rhs_x,
                  double *sol_y, double *sol_x);
+/* The reference's MAX_ITER is a compile-time 200; fixtures of mid-solve iterates stop earlier. */
+void kko_set_itnlim(int itnlim);
 /* wall-clock seconds spent inside ldltfac / forwardbackward during the last kko_solver_* call */
 void kko_last_timing(double *t_factor, double *t_solve, int *n_factor, int *n_solve, int *n_rawsolve);
 

@@ -37,6 +37,8 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 
+struct double2 { double x, y; };
+
 namespace emu {
 struct Cta {
     std::unique_ptr<std::barrier<>> bar;
