@@ -1,6 +1,7 @@
 // vbk_kkt.cu -- host orchestration of the device-resident factor object (see vbk_kkt.h).
 #include "vbk_kkt.h"
 #include "vbk_kernels.cuh"
+#include "vbk_factor_tiled.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -154,6 +155,45 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
 #ifdef VBK_EMU
     solve_grid_ = std::min(solve_grid_, 3);
 #endif
+
+    // second-generation strict kernels: task tables, pivot hand-off arrays, launch geometry
+    {
+        const char* ef = std::getenv("VBK_FACTOR");
+        const char* es = std::getenv("VBK_SOLVE");
+        use_tiled_ = !(ef && std::strcmp(ef, "simple") == 0);
+        use_flags_ = !(es && std::strcmp(es, "simple") == 0);
+        const int ntasks = sym_.ntasks();
+        int max_slices = 1, max_cnt = 1;
+        for (int j = 0; j < N; ++j) max_slices = std::max(max_slices, sym_.col_ntask[j]);
+        for (int t = 0; t < ntasks; ++t) max_cnt = std::max(max_cnt, sym_.task_cnt[t]);
+        task_col_.upload(sym_.task_col, stream_); task_blk_.upload(sym_.task_blk, stream_);
+        task_pos0_.upload(sym_.task_pos0, stream_); task_cnt_.upload(sym_.task_cnt, stream_);
+        col_task0_.upload(sym_.col_task0, stream_); col_ntask_.upload(sym_.col_ntask, stream_);
+        if (!sym_.winptr.empty()) winptr_.upload(sym_.winptr, stream_); else winptr_.alloc(1);
+        col_left_.alloc(N); col_ready_.alloc(N); piv_flag_.alloc(N); piv_keep_.alloc(N); done_.alloc(N);
+        piv_val_.alloc(N); task_max_.alloc(std::max(ntasks, 1));
+        temp_cap_ = std::max(max_cnt, 32);
+        tile_doubles_ = std::max(8192, temp_cap_);
+        tiled_smem_ = sizeof(double) * ((size_t)tile_doubles_ + temp_cap_ + 2 * kTileMaxBatch + kTiledThreads + 2) +
+                      sizeof(int) * ((size_t)2 * kTileMaxBatch + 1 + sym_.rowblk + 8);
+#ifndef VBK_EMU
+        VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_));
+#endif
+        int occ2 = 1;
+        VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_factor_tiled, kTiledThreads, tiled_smem_));
+        occ2 = std::max(1, std::min(occ2, 3));
+        long long g2 = (long long)num_sms_ * occ2;
+        if (g2 * (long long)N * 4 > budget) g2 = std::max<long long>(num_sms_ / 2, budget / ((long long)N * 4));
+        g2 = std::max<long long>(1, std::min<long long>(g2, ntasks));
+#ifdef VBK_EMU
+        g2 = std::max(1, std::min(3, ntasks));
+#endif
+        // a dependent pivot makes the first slice of a column wait for all its sibling slices, so
+        // every slice of one column must be able to be resident at the same time
+        g2 = std::max<long long>(g2, std::min<long long>(ntasks, max_slices + 1));
+        tiled_grid_ = (int)g2;
+        if ((size_t)tiled_grid_ > (size_t)factor_grid_) slotmap_.alloc((size_t)tiled_grid_ * N);
+    }
     VBK_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -201,9 +241,34 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
     VBK_CUDA(cudaMemsetAsync(L_.p, 0, sizeof(double) * (size_t)lnz, stream_));
     VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapA_.p, A_val_.p, L_.p);
     VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapAt_.p, At_val_.p, L_.p);
+    if (use_tiled_) {
+        // K2/K4 numeric LDL^T, batched-tile / sliced-column kernel (vbk_factor_tiled.cuh)
+        VBK_LAUNCH(k_tiled_reset, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, col_ntask_.p, pend_.p,
+                   col_left_.p, col_ready_.p, piv_flag_.p, counters_.p);
+        TiledArgs ta;
+        ta.N = N; ta.n_ld = n; ta.ntasks = sym_.ntasks(); ta.tile_doubles = tile_doubles_; ta.temp_cap = temp_cap_;
+        ta.kL = kL_.p; ta.iL = iL_.p; ta.L = L_.p; ta.diag = diag_.p; ta.mark = mark_.p;
+        ta.rowptr = rowptr_.p; ta.rk = rk_sig_.p; ta.rj = rj_sig_.p;
+        ta.parent = parent_.p; ta.perm = perm_.p;
+        ta.task_col = task_col_.p; ta.task_blk = task_blk_.p; ta.task_pos0 = task_pos0_.p; ta.task_cnt = task_cnt_.p;
+        ta.col_task0 = col_task0_.p; ta.col_ntask = col_ntask_.p;
+        ta.winptr = winptr_.p; ta.nblk = sym_.nblk; ta.rowblk = sym_.rowblk; ta.slice_row0 = sym_.slice_row0;
+        ta.pend = pend_.p; ta.col_left = col_left_.p; ta.col_ready = col_ready_.p; ta.piv_flag = piv_flag_.p;
+        ta.piv_val = piv_val_.p; ta.piv_keep = piv_keep_.p; ta.task_max = task_max_.p;
+        ta.counters = counters_.p; ta.scal_bits = bits_.p; ta.epsnum = 0.0;       // _EPSNUM, ldlt.c:29
+        ta.slotmap = slotmap_.p;
+        VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
+        VBK_LAUNCH(k_factor_tiled, tiled_grid_, kTiledThreads, tiled_smem_, stream_, ta);
+        VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
+        VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);
+        VBK_LAUNCH(k_update_epsdiag, 1, 32, 0, stream_, scal_.p, bits_.p);
+        VBK_CHECK_LAUNCH();
+        stats.kernel_launches += 9;
+        return;
+    }
     VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, 0, pend_.p, counters_.p, 1);
 
-    // K2/K4 numeric LDL^T
+    // K2/K4 numeric LDL^T, first-generation kernel (one barrier per contributor)
     FactorArgs fa;
     fa.N = N; fa.n_ld = n; fa.maxcol = std::max(sym_.maxcol, 1); fa.smem_slots = smem_slots_;
     fa.kL = kL_.p; fa.iL = iL_.p; fa.L = L_.p; fa.diag = diag_.p; fa.mark = mark_.p;
@@ -238,6 +303,22 @@ void Kkt::rawsolve_dev()
     // eps = epssol*maxv(z,m) is only used when the factorisation met dependent pivots (ldlt.c:446)
     VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_ZMAX, 1);
     VBK_LAUNCH(k_absmax, vec_grid(sym_.m), kVecThreads, 0, stream_, sym_.m, z_.p, bits_.p + S_ZMAX);
+    if (use_flags_) {
+        // per-column completion flags, shared-memory subtract chains (vbk_factor_tiled.cuh)
+        FlagSolveArgs fs;
+        fs.N = N; fs.kL = kL_.p; fs.iL = iL_.p; fs.L = L_.p; fs.diag = diag_.p; fs.mark = mark_.p;
+        fs.rowptr = rowptr_.p; fs.rk = rk_asc_.p; fs.rj = rj_asc_.p; fs.parent = parent_.p;
+        fs.z = z_.p; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
+        const size_t sm = (size_t)(kSolveThreads / 32) * 32 * (sizeof(double) + sizeof(int));
+        VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
+        VBK_LAUNCH(k_fwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
+        VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
+        VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
+        VBK_LAUNCH(k_bwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
+        VBK_CHECK_LAUNCH();
+        stats.kernel_launches += 7;
+        return;
+    }
     VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, 0, pend_.p, counters_.p, 2);
     VBK_LAUNCH(k_fwd_strict, solve_grid_, kSolveThreads, 0, stream_, sa);
     VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);

@@ -122,6 +122,14 @@ private:
     double* pin_scal_ = nullptr;
     int* pin_cnt_ = nullptr;
 
+    // second-generation strict kernels (vbk_factor_tiled.cuh); $VBK_FACTOR=simple / $VBK_SOLVE=simple
+    // select the first-generation kernels of vbk_kernels.cuh for A/B checks
+    bool use_tiled_ = true, use_flags_ = true;
+    DevArray<int> task_col_, task_blk_, task_pos0_, task_cnt_, col_task0_, col_ntask_, winptr_;
+    DevArray<int> col_left_, col_ready_, piv_flag_, piv_keep_, done_;
+    DevArray<double> piv_val_, task_max_;
+    int tiled_grid_ = 1, tile_doubles_ = 8192, temp_cap_ = 512;
+    size_t tiled_smem_ = 0;
     int factor_grid_ = 1, solve_grid_ = 1;
     cudaEvent_t ev_f0_ = nullptr, ev_f1_ = nullptr;
     size_t factor_smem_ = 0;

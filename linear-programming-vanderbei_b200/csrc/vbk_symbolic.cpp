@@ -296,6 +296,51 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
         }
     }
 
+    // task decomposition for the numeric kernels (see vbk_symbolic.h)
+    if (const char* e = std::getenv("VBK_WHOLE_CAP")) whole_cap = std::max(1, std::atoi(e)); else whole_cap = 512;
+    slice_row0 = N;
+    for (int j = 0; j < N; ++j)
+        if (kL[j + 1] - kL[j] > whole_cap) { slice_row0 = j; break; }
+    if (const char* e = std::getenv("VBK_ROWBLK")) rowblk = std::max(1, std::atoi(e)); else rowblk = 64;
+    nblk = 0;
+    winptr.clear();
+    if (slice_row0 < N) {
+        nblk = (N - slice_row0 + rowblk - 1) / rowblk;
+        while ((long long)N * (nblk + 1) > (1LL << 28)) {   // keep the lookup table below 1 GiB
+            rowblk *= 2;
+            nblk = (N - slice_row0 + rowblk - 1) / rowblk;
+        }
+        winptr.assign((size_t)N * (nblk + 1), 0);
+        for (int j = 0; j < N; ++j) {
+            int* wp = &winptr[(size_t)j * (nblk + 1)];
+            int k = kL[j];
+            for (int b = 0; b <= nblk; ++b) {
+                long long bound = (long long)slice_row0 + (long long)b * rowblk;
+                while (k < kL[j + 1] && iL[k] < bound) ++k;
+                wp[b] = (b == nblk) ? kL[j + 1] : k;
+            }
+        }
+    }
+    task_col.clear(); task_blk.clear(); task_pos0.clear(); task_cnt.clear();
+    col_task0.assign(N, 0);
+    col_ntask.assign(N, 0);
+    for (int j = 0; j < N; ++j) {
+        col_task0[j] = (int)task_col.size();
+        const int c = kL[j + 1] - kL[j];
+        if (c <= whole_cap) {
+            task_col.push_back(j); task_blk.push_back(-1); task_pos0.push_back(kL[j]); task_cnt.push_back(c);
+        } else {
+            const int* wp = &winptr[(size_t)j * (nblk + 1)];
+            for (int b = 0; b < nblk; ++b) {
+                int p0 = wp[b], p1 = wp[b + 1];
+                if (p1 > p0) {
+                    task_col.push_back(j); task_blk.push_back(b); task_pos0.push_back(p0); task_cnt.push_back(p1 - p0);
+                }
+            }
+        }
+        col_ntask[j] = (int)task_col.size() - col_task0[j];
+    }
+
     // fundamental supernodes: column j+1 continues j's supernode when j+1 is j's only-child parent
     // and struct(j+1) = struct(j) \ {j+1}
     sn_ptr.clear();

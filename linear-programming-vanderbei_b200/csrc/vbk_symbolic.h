@@ -42,6 +42,19 @@ struct Symbolic {
     // scatter maps for inv_num (ldlt.c:243-269): L position of every stored entry of A / At, or -1
     std::vector<int> mapA, mapAt;
 
+    // ---- task decomposition of the numeric factorisation (GPU scheduling, not in the reference) ----
+    // A column with at most whole_cap rows is one task.  Longer columns are cut by global row
+    // blocks of `rowblk` rows counted from row `slice_row0` (the first long column): one task per
+    // block in which the column has rows, so that several CTAs share a long column.  winptr[j*(nblk+1)+b]
+    // is the first position in column j whose row is >= slice_row0 + b*rowblk: every contributing
+    // column finds its entries for a block by lookup, never by search.
+    int whole_cap = 512;              // $VBK_WHOLE_CAP overrides (tests force slicing on tiny LPs)
+    int slice_row0 = 0, rowblk = 64, nblk = 0;
+    std::vector<int> winptr;          // [N*(nblk+1)], empty when no column is sliced
+    std::vector<int> task_col, task_blk, task_pos0, task_cnt;   // blk = -1: whole column
+    std::vector<int> col_task0, col_ntask;                      // [N]
+    int ntasks() const { return (int)task_col.size(); }
+
     // fundamental supernodes: column ranges [sn_ptr[s], sn_ptr[s+1])
     std::vector<int> sn_ptr;
     std::vector<int> sn_of;         // supernode of each column

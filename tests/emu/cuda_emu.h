@@ -115,6 +115,10 @@ template <class T> inline T emu_shfl_from(T v, int srclane) {
 }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl_from(v, src & 31); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { return emu_shfl_from(v, (int)(threadIdx.x % 32 + d)); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+    int lane = (int)(threadIdx.x % 32);
+    return emu_shfl_from(v, lane >= (int)d ? lane - (int)d : lane);
+}
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl_from(v, (int)((threadIdx.x % 32) ^ m)); }
 
 inline double __dmul_rn(double a, double b) { return a * b; }

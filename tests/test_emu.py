@@ -32,6 +32,22 @@ def test_emu_kkt_step_bit_exact(vbkkt, emu_lib, oracle_lib, method, it):
         assert info["passes"] == 2
 
 
+@pytest.mark.parametrize("cap,blk", [(4, 4), (2, 3)])
+def test_emu_sliced_columns_bit_exact(vbkkt, emu_lib, oracle_lib, monkeypatch, cap, blk):
+    """Force the long-column path (several CTAs share one column, pivot hand-off between slices,
+    dependent-pivot rule across slices) on a tiny LP by lowering the slicing thresholds."""
+    monkeypatch.setenv("VBK_WHOLE_CAP", str(cap))
+    monkeypatch.setenv("VBK_ROWBLK", str(blk))
+    info = P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("afiro"), "hsd", 26)
+    assert info["ndep"] > 0
+
+
+@pytest.mark.parametrize("which", ["VBK_FACTOR", "VBK_SOLVE"])
+def test_emu_first_generation_kernels_still_bit_exact(vbkkt, emu_lib, oracle_lib, monkeypatch, which):
+    monkeypatch.setenv(which, "simple")
+    P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("afiro"), "hsd", 26)
+
+
 def test_emu_kkt_step_second_problem(vbkkt, emu_lib, oracle_lib):
     P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("sc50b"), "hsd", 10)
 
