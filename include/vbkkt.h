@@ -115,6 +115,9 @@ int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const i
 void vbk_set_iteration_limit(int itnlim);
 /* device time (ms, CUDA events on the handle's stream) of the last numeric-factor kernel */
 float vbk_kkt_last_factor_kernel_ms(vbk_kkt *h);
+/* with $VBK_PROF set: SM cycles per phase of the tiled factor kernel since the last call (8 counters:
+ * claim+init, wait, stage, scan, scatter, accumulate, pivot, write) */
+void vbk_kkt_phase_profile(vbk_kkt *h, unsigned long long *out8);
 /* roofline yardsticks measured on the spot: FP64 DFMA TFLOP/s and device copy GB/s */
 double vbk_measure_fp64_tflops(int device);
 double vbk_measure_hbm_gbs(int device);

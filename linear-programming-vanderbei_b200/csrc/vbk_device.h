@@ -34,6 +34,14 @@
 
 #define VBK_CHECK_LAUNCH() VBK_CUDA(cudaGetLastError())
 
+__device__ __forceinline__ long long vbk_clock() {
+#ifdef VBK_EMU
+    return 0;
+#else
+    return clock64();
+#endif
+}
+
 // volatile (L1-bypassing, non-cached) load used by the dataflow waits
 __device__ __forceinline__ int vbk_ld_volatile(const int* p) {
 #ifdef VBK_EMU

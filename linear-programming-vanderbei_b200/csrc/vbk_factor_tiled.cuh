@@ -44,6 +44,7 @@ struct TiledArgs {
     double* piv_val; int* piv_keep; double* task_max;
     int* counters; const unsigned long long* scal_bits; double epsnum;
     int* slotmap;       // [gridDim.x][N]
+    unsigned long long* prof;   // optional [8] cycle counters per phase (thread 0 of every CTA), or null
 };
 
 // per-launch reset of the tiled factor's dataflow state
@@ -80,6 +81,12 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
 
     for (int q = tid; q < a.tile_doubles; q += nt) tile[q] = 0.0;   // consumed entries are re-zeroed below
 
+    // optional phase profile: 0 claim+init, 1 wait for children, 2 stage, 3 scan, 4 scatter,
+    // 5 accumulate, 6 pivot (reduce + hand-off), 7 write+release
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = vbk_clock();
+#define VBK_TICK(slot) do { if (a.prof && tid == 0) { long long now_ = vbk_clock(); pacc[slot] += now_ - tlast; tlast = now_; } } while (0)
+
     for (;;) {
         __syncthreads();
         if (tid == 0) s_ctl[0] = atomicAdd(&a.counters[C_NEXT], 1);
@@ -101,11 +108,13 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
         int B = cnt > 0 ? a.tile_doubles / cnt : kTileMaxBatch;
         if (B > kTileMaxBatch) B = kTileMaxBatch;
 
+        VBK_TICK(0);
         if (tid == 0) {               // every etree child final => every contributing column final
             while (vbk_ld_volatile(&a.pend[i]) != 0) __nanosleep(64);
             __threadfence();
         }
         __syncthreads();
+        VBK_TICK(1);
 
         double diagi = 0.0;
         if (first && tid == nt - 1) diagi = __ldcg(&a.diag[i]);
@@ -131,6 +140,7 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
             }
             if (tid == 0) s_off[0] = 0;
             __syncthreads();
+            VBK_TICK(2);
             if (tid < 32) {                                            // inclusive scan of <=128 counts
                 int v[4], sum = 0;
 #pragma unroll
@@ -143,26 +153,46 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
                 for (int u = 0; u < 4; ++u) { int idx = lane * 4 + u; run += v[u]; if (idx < nb) s_off[idx + 1] = run; }
             }
             __syncthreads();
+            VBK_TICK(3);
             // -- scatter all products of the batch into the tile; every load is independent
             const int E = s_off[nb];
-            for (int e = tid; e < E; e += nt) {
-                int lo = 0, hi = nb;                                   // largest q with s_off[q] <= e
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid; }
-                const int kk = s_kb[lo] + (e - s_off[lo]);
-                const int row = a.iL[kk];
-                const int sl = (blk < 0) ? myslot[row] : blockmap[row - bs];
-                tile[lo * cnt + sl] = s_w[lo] * __ldcg(&a.L[kk]);      // lij_dj*AAt[kk], ldlt.c:583
+            constexpr int U = 8;       // elements in flight per thread: the loads of a group overlap
+            for (int e0 = tid; e0 < E; e0 += nt * U) {
+                int qq[U], kk[U], row[U], sl[U];
+                double val[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * nt;
+                    kk[u] = -1;
+                    qq[u] = 0;
+                    if (e < E) {
+                        int lo = 0, hi = nb;                           // largest q with s_off[q] <= e
+                        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid; }
+                        qq[u] = lo;
+                        kk[u] = s_kb[lo] + (e - s_off[lo]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (kk[u] >= 0) { row[u] = a.iL[kk[u]]; val[u] = __ldcg(&a.L[kk[u]]); }
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (kk[u] >= 0) sl[u] = (blk < 0) ? myslot[row[u]] : blockmap[row[u] - bs];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (kk[u] >= 0) tile[qq[u] * cnt + sl[u]] = s_w[qq[u]] * val[u];   // lij_dj*AAt[kk], ldlt.c:583
             }
             __syncthreads();
+            VBK_TICK(4);
             // -- each slot's owner replays the batch in contributor order; the tile is left zeroed
             for (int s = tid; s < cnt; s += nt) {
                 double acc = temp[s];
+#pragma unroll 8
                 for (int q = 0; q < nb; ++q) { acc += tile[q * cnt + s]; tile[q * cnt + s] = 0.0; }
                 temp[s] = acc;
             }
             if (first && tid == nt - 1)
                 for (int q = 0; q < nb; ++q) diagi -= s_l[q] * s_w[q];   // ldlt.c:573
             __syncthreads();
+            VBK_TICK(5);
         }
 
         // L[:,i] -= temp (ldlt.c:596-599); max|.| of this slice for the dependent-pivot rule
@@ -173,14 +203,13 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
             double av = fabs(v);
             if (av > mymax) mymax = av;
         }
-        s_red[tid] = mymax;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { double o = __shfl_xor_sync(0xffffffffu, mymax, d); if (o > mymax) mymax = o; }
+        if (lane == 0) s_red[tid >> 5] = mymax;
         if (first && tid == nt - 1) s_dbl[1] = diagi;
         __syncthreads();
-        for (int s = nt / 2; s > 0; s >>= 1) {
-            if (tid < s && s_red[tid + s] > s_red[tid]) s_red[tid] = s_red[tid + s];
-            __syncthreads();
-        }
         if (tid == 0) {
+            for (int wv = 1; wv < (nt >> 5); ++wv) if (s_red[wv] > s_red[0]) s_red[0] = s_red[wv];
             if (nslices > 1) {
                 a.task_max[t] = s_red[0];
                 __threadfence();
@@ -220,6 +249,7 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
             s_ctl[2] = keep;
         }
         __syncthreads();
+        VBK_TICK(6);
         const double piv = s_dbl[0];
         const int keep = s_ctl[2];
         for (int s = tid; s < cnt; s += nt) a.L[p0 + s] = keep ? temp[s] / piv : 0.0;   // ldlt.c:621-627
@@ -233,7 +263,11 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
                 if (p >= 0) atomicSub(&a.pend[p], 1);
             }
         }
+        VBK_TICK(7);
     }
+    if (a.prof && tid == 0)
+        for (int u = 0; u < 8; ++u) atomicAdd(&a.prof[u], (unsigned long long)pacc[u]);
+#undef VBK_TICK
 }
 
 // --------------------------------------------------------------------------------------------
@@ -261,6 +295,22 @@ static __global__ void k_flags_reset(int N, int* __restrict__ done, int* __restr
     }
 }
 
+// acc - p[0] - p[1] - ... strictly left to right; a full batch is loaded first (32 independent
+// shared-memory reads) so that only the 32 dependent subtractions remain on the critical path
+__device__ __forceinline__ double chain_sub(double acc, const double* p, int cnt)
+{
+    if (cnt == 32) {
+        double v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = p[q];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc = acc - v[q];
+    } else {
+        for (int q = 0; q < cnt; ++q) acc = acc - p[q];
+    }
+    return acc;
+}
+
 __device__ __forceinline__ double flag_solve_eps(const FlagSolveArgs& a) {
     return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;   // ldlt.c:446
 }
@@ -270,7 +320,6 @@ static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArg
     VBK_DYN_SMEM(raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* sp = reinterpret_cast<double*>(raw) + warp * 32;                    // products
-    int* sok = reinterpret_cast<int*>(reinterpret_cast<double*>(raw) + (blockDim.x >> 5) * 32) + warp * 32;
     const double eps = flag_solve_eps(a);
     for (;;) {
         int r = 0;
@@ -281,22 +330,17 @@ static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArg
         const int rb = a.rowptr[r], re = a.rowptr[r + 1];
         for (int t0 = rb; t0 < re; t0 += 32) {
             const int t = t0 + lane;
-            double p = 0.0;
-            int ok = 0;
+            double p = 0.0;        // an unmarked column contributes nothing (ldlt.c:455); x - (+0.0) == x
             if (t < re) {
                 const int j = a.rj[t];
                 const double l = a.L[a.rk[t]];
                 while (vbk_ld_volatile(&a.done[j]) == 0) __nanosleep(20);
                 __threadfence();
-                if (a.mark[j]) { p = l * __ldcg(&a.z[j]); ok = 1; }
+                if (a.mark[j]) p = l * __ldcg(&a.z[j]);
             }
             sp[lane] = p;
-            sok[lane] = ok;
             __syncwarp();
-            if (lane == 0) {
-                const int cnt = (re - t0 < 32) ? (re - t0) : 32;
-                for (int q = 0; q < cnt; ++q) if (sok[q]) acc = acc - sp[q];    // z[row] -= AAt[k]*beta
-            }
+            if (lane == 0) acc = chain_sub(acc, sp, (re - t0 < 32) ? (re - t0) : 32);   // z[row] -= AAt[k]*beta
             __syncwarp();
         }
         if (lane == 0) {
@@ -314,7 +358,7 @@ static __global__ void __launch_bounds__(kSolveThreads) k_bwd_flags(FlagSolveArg
 {
     VBK_DYN_SMEM(raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sp = reinterpret_cast<double*>(raw) + warp * 32;
+    double* sp = reinterpret_cast<double*>(raw) + warp * 128;
     const double eps = flag_solve_eps(a);
     for (;;) {
         int c = 0;
@@ -331,17 +375,33 @@ static __global__ void __launch_bounds__(kSolveThreads) k_bwd_flags(FlagSolveArg
         double beta = a.z[i];                        // z[i] after the diagonal sweep (previous launch)
         if (a.mark[i]) {
             const int kb = a.kL[i], ke = a.kL[i + 1];
-            double pnext = 0.0;
-            if (kb + lane < ke) pnext = a.L[kb + lane] * __ldcg(&a.z[a.iL[kb + lane]]);
-            for (int k0 = kb; k0 < ke; k0 += 32) {
-                sp[lane] = pnext;
-                const int kn = k0 + 32 + lane;                                   // prefetch the next batch
-                pnext = 0.0;
-                if (kn < ke) pnext = a.L[kn] * __ldcg(&a.z[a.iL[kn]]);
+            // 128 entries per round: the raw operands of the NEXT round are loaded before the dependent
+            // subtract chain of the current one and multiplied only afterwards, so the two L2 round
+            // trips (iL -> z) hide behind the chain instead of stalling it
+            double ln[4], zn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u * 32 + lane;
+                ln[u] = 0.0; zn[u] = 0.0;
+                if (k < ke) { ln[u] = a.L[k]; zn[u] = __ldcg(&a.z[a.iL[k]]); }
+            }
+            for (int k0 = kb; k0 < ke; k0 += 128) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sp[u * 32 + lane] = ln[u] * zn[u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + 128 + u * 32 + lane;
+                    ln[u] = 0.0; zn[u] = 0.0;
+                    if (k < ke) { ln[u] = a.L[k]; zn[u] = __ldcg(&a.z[a.iL[k]]); }
+                }
                 __syncwarp();
                 if (lane == 0) {
-                    const int cnt = (ke - k0 < 32) ? (ke - k0) : 32;
-                    for (int q = 0; q < cnt; ++q) beta = beta - sp[q];           // ldlt.c:494
+                    const int rem = ke - k0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = rem - u * 32;
+                        if (c > 0) beta = chain_sub(beta, sp + u * 32, c < 32 ? c : 32);     // ldlt.c:494
+                    }
                 }
                 __syncwarp();
             }

@@ -172,6 +172,7 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
         if (!sym_.winptr.empty()) winptr_.upload(sym_.winptr, stream_); else winptr_.alloc(1);
         col_left_.alloc(N); col_ready_.alloc(N); piv_flag_.alloc(N); piv_keep_.alloc(N); done_.alloc(N);
         piv_val_.alloc(N); task_max_.alloc(std::max(ntasks, 1));
+        if (std::getenv("VBK_PROF")) { prof_.alloc(8); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 64, stream_)); }
         temp_cap_ = std::max(max_cnt, 32);
         tile_doubles_ = std::max(8192, temp_cap_);
         tiled_smem_ = sizeof(double) * ((size_t)tile_doubles_ + temp_cap_ + 2 * kTileMaxBatch + kTiledThreads + 2) +
@@ -212,6 +213,15 @@ float Kkt::last_factor_kernel_ms()
     VBK_CUDA(cudaEventSynchronize(ev_f1_));
     VBK_CUDA(cudaEventElapsedTime(&ms, ev_f0_, ev_f1_));
     return ms;
+}
+
+void Kkt::read_phase_profile(unsigned long long out[8])
+{
+    for (int u = 0; u < 8; ++u) out[u] = 0;
+    if (!prof_.p) return;
+    prof_.download(out, 8, stream_);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+    VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 64, stream_));
 }
 
 double Kkt::epsdiag() { require_device("epsdiag"); read_scalars(); return pin_scal_[S_EPSDIAG]; }
@@ -257,6 +267,7 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
         ta.piv_val = piv_val_.p; ta.piv_keep = piv_keep_.p; ta.task_max = task_max_.p;
         ta.counters = counters_.p; ta.scal_bits = bits_.p; ta.epsnum = 0.0;       // _EPSNUM, ldlt.c:29
         ta.slotmap = slotmap_.p;
+        ta.prof = prof_.p;
         VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
         VBK_LAUNCH(k_factor_tiled, tiled_grid_, kTiledThreads, tiled_smem_, stream_, ta);
         VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
@@ -309,7 +320,7 @@ void Kkt::rawsolve_dev()
         fs.N = N; fs.kL = kL_.p; fs.iL = iL_.p; fs.L = L_.p; fs.diag = diag_.p; fs.mark = mark_.p;
         fs.rowptr = rowptr_.p; fs.rk = rk_asc_.p; fs.rj = rj_asc_.p; fs.parent = parent_.p;
         fs.z = z_.p; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
-        const size_t sm = (size_t)(kSolveThreads / 32) * 32 * (sizeof(double) + sizeof(int));
+        const size_t sm = (size_t)(kSolveThreads / 32) * 128 * sizeof(double);
         VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
         VBK_LAUNCH(k_fwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
         VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);

@@ -85,6 +85,9 @@ public:
     KktStats stats;
     // device time of the last numeric-factor kernel (CUDA events on the handle's stream), ms
     float last_factor_kernel_ms();
+    // $VBK_PROF=1: cycles spent per phase by thread 0 of every CTA of the tiled factor kernel since the
+    // last call (8 counters, see vbk_factor_tiled.cuh); zeros when profiling is off
+    void read_phase_profile(unsigned long long out[8]);
 
     int num_sms() const { return num_sms_; }
     int vec_grid(long long n) const;
@@ -128,6 +131,7 @@ private:
     DevArray<int> task_col_, task_blk_, task_pos0_, task_cnt_, col_task0_, col_ntask_, winptr_;
     DevArray<int> col_left_, col_ready_, piv_flag_, piv_keep_, done_;
     DevArray<double> piv_val_, task_max_;
+    DevArray<unsigned long long> prof_;   // $VBK_PROF: per-phase cycle counters of the tiled factor kernel
     int tiled_grid_ = 1, tile_doubles_ = 8192, temp_cap_ = 512;
     size_t tiled_smem_ = 0;
     int factor_grid_ = 1, solve_grid_ = 1;

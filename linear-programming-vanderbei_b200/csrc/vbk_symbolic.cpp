@@ -297,11 +297,11 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
     }
 
     // task decomposition for the numeric kernels (see vbk_symbolic.h)
-    if (const char* e = std::getenv("VBK_WHOLE_CAP")) whole_cap = std::max(1, std::atoi(e)); else whole_cap = 512;
+    if (const char* e = std::getenv("VBK_WHOLE_CAP")) whole_cap = std::max(1, std::atoi(e)); else whole_cap = 64;
     slice_row0 = N;
     for (int j = 0; j < N; ++j)
         if (kL[j + 1] - kL[j] > whole_cap) { slice_row0 = j; break; }
-    if (const char* e = std::getenv("VBK_ROWBLK")) rowblk = std::max(1, std::atoi(e)); else rowblk = 64;
+    if (const char* e = std::getenv("VBK_ROWBLK")) rowblk = std::max(1, std::atoi(e)); else rowblk = 32;   // measured on B200: 32 beats 64 (profiles/)
     nblk = 0;
     winptr.clear();
     if (slice_row0 < N) {
