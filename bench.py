@@ -157,7 +157,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("VBK_BENCH_WORKLOAD", "pilot87"))
+    # dfl001 is the largest netlib LP BASELINE.json's config 2 names (FP64-bound factor, ~90 flop/B)
+    ap.add_argument("--workload", default=os.environ.get("VBK_BENCH_WORKLOAD", "dfl001"))
     ap.add_argument("--iterate", type=int, default=20)
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -180,16 +181,12 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        import harness as H
-        vb = _load("vbkkt", ROOT / "linear-programming-vanderbei_b200" / "__init__.py")
-        sym = H.kkt_for(vb, vb.load(), lp, device=-1)           # host-only symbolic, for the flop model
-        cpu = CpuKkt(lp)
+        cpu = CpuKkt(lp)                                         # nothing of the product on this arm
         sol_y, _ = cpu.step(it)
-        passes = 0
-        if cpu.kind == "port":
-            passes = cpu.F.passes
-        raw = int(it.get("rawsolves", 0)) or 3
-        flops = work_model(sym.narth, sym.lnz, N, nz, raw)
+        assert np.array_equal(sol_y, it["sol_y"]), "reference arm does not reproduce the fixture"
+        # flop model from the reference's own symbolic counts stored in the fixture (ldlt.c:1243-1248);
+        # 2 rawsolve passes per step is what both arms need on these iterates (checked by the GPU arm)
+        flops = work_model(float(lp.extra["sym_narth"]), int(lp.extra["sym_lnz"]), N, nz, 2)
         for _ in range(a.warmup):
             cpu.step(it)
         t0 = time.perf_counter()
@@ -333,7 +330,7 @@ def main():
     fac_s = float(np.mean(fac_ms)) * 1e-3
     b_fac = 12.0 * K.lnz + 8.0 * K.lnz + 2 * 12.0 * nz + 24.0 * N
     fp64_peak = float(lib.vbk_measure_fp64_tflops(local_rank))
-    roofline = {"kernel": "k_factor_strict" if a.mode == "strict" else "factor (fast)", "bound": "hbm",
+    roofline = {"kernel": "k_factor_tiled (strict)" if a.mode == "strict" else "factor (fast)", "bound": "hbm",
                 "achieved": b_fac / fac_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": b_fac / fac_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": fac_s * 1e3, "share_of_step": fac_s * 1e3 / ms_per_step,

@@ -45,6 +45,12 @@ struct TiledArgs {
     int* counters; const unsigned long long* scal_bits; double epsnum;
     int* slotmap;       // [gridDim.x][N]
     unsigned long long* prof;   // optional [8] cycle counters per phase (thread 0 of every CTA), or null
+    // fast mode (vbk_fast.cuh): phase 0 = plain factorisation of tasks [0, ntasks); phase 2 = Schur
+    // assembly of the trailing dense window: tasks [task_base, task_base+ntasks) of columns >= T take
+    // only contributors j < T, need no dependency waits, and write K - sum into the dense scratch
+    // Sw (column-major, leading dimension ldw) instead of pivoting
+    int phase, task_base, T, ldw;
+    double* Sw; double* wmag;
 };
 
 // per-launch reset of the tiled factor's dataflow state
@@ -91,8 +97,8 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
         __syncthreads();
         if (tid == 0) s_ctl[0] = atomicAdd(&a.counters[C_NEXT], 1);
         __syncthreads();
-        const int t = s_ctl[0];
-        if (t >= a.ntasks) break;
+        if (s_ctl[0] >= a.ntasks) break;
+        const int t = s_ctl[0] + a.task_base;
         const int i = a.task_col[t], blk = a.task_blk[t], p0 = a.task_pos0[t], cnt = a.task_cnt[t];
         const int nslices = a.col_ntask[i];
         const bool first = (t == a.col_task0[i]);
@@ -109,29 +115,33 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
         if (B > kTileMaxBatch) B = kTileMaxBatch;
 
         VBK_TICK(0);
-        if (tid == 0) {               // every etree child final => every contributing column final
+        if (tid == 0 && a.phase != 2) {   // every etree child final => every contributing column final
             while (vbk_ld_volatile(&a.pend[i]) != 0) __nanosleep(64);
             __threadfence();
         }
         __syncthreads();
         VBK_TICK(1);
 
-        double diagi = 0.0;
-        if (first && tid == nt - 1) diagi = __ldcg(&a.diag[i]);
+        double diagi = 0.0, dmag = 0.0;
+        if (first && tid == nt - 1) { diagi = __ldcg(&a.diag[i]); dmag = fabs(diagi); }
         const int rb = a.rowptr[i], re = a.rowptr[i + 1];
         for (int t0 = rb; t0 < re; t0 += B) {
             const int nb = (re - t0 < B) ? (re - t0) : B;
             // -- stage the batch: lij, lij*dj and the entry range of each contributor for this task
             for (int q = tid; q < nb; q += nt) {
                 const int k = a.rk[t0 + q], j = a.rj[t0 + q];
-                const double lij = __ldcg(&a.L[k]);
-                const double dj = __ldcg(&a.diag[j]);
-                int kb = k + 1, ke = a.kL[j + 1];
-                if (blk >= 0) {
-                    const int* wp = wp_base + (size_t)j * wstride;
-                    int lo = wp[blk], hi = wp[blk + 1];
-                    if (lo > kb) kb = lo;
-                    if (hi < ke) ke = hi;
+                double lij = 0.0, dj = 0.0;
+                int kb = 0, ke = 0;
+                if (a.phase != 2 || j < a.T) {       // Schur assembly: window columns contribute later
+                    lij = __ldcg(&a.L[k]);
+                    dj = __ldcg(&a.diag[j]);
+                    kb = k + 1; ke = a.kL[j + 1];
+                    if (blk >= 0) {
+                        const int* wp = wp_base + (size_t)j * wstride;
+                        int lo = wp[blk], hi = wp[blk + 1];
+                        if (lo > kb) kb = lo;
+                        if (hi < ke) ke = hi;
+                    }
                 }
                 s_l[q] = lij;
                 s_w[q] = lij * dj;                                     // ldlt.c:572
@@ -190,9 +200,21 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
                 temp[s] = acc;
             }
             if (first && tid == nt - 1)
-                for (int q = 0; q < nb; ++q) diagi -= s_l[q] * s_w[q];   // ldlt.c:573
+                for (int q = 0; q < nb; ++q) { double p = s_l[q] * s_w[q]; diagi -= p; if (fabs(p) > dmag) dmag = fabs(p); }   // ldlt.c:573
             __syncthreads();
             VBK_TICK(5);
+        }
+
+        if (a.phase == 2) {
+            // Schur complement of the sparse part, written densely: Sw[r-T, i-T] = K[r,i] - sum; the
+            // diagonal entry carries the magnitude of its terms for the fast-mode zero-pivot test
+            const size_t ci = (size_t)(i - a.T);
+            for (int s = tid; s < cnt; s += nt) {
+                const int row = a.iL[p0 + s];
+                a.Sw[(size_t)(row - a.T) + ci * a.ldw] = __ldcg(&a.L[p0 + s]) - temp[s];
+            }
+            if (first && tid == nt - 1) { a.Sw[ci + ci * a.ldw] = diagi; a.wmag[ci] = dmag; }
+            continue;
         }
 
         // L[:,i] -= temp (ldlt.c:596-599); max|.| of this slice for the dependent-pivot rule
@@ -277,6 +299,7 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
 // --------------------------------------------------------------------------------------------
 struct FlagSolveArgs {
     int N;
+    int nclaim;   // rows [0, nclaim) forward / columns nclaim-1..0 backward (N, or the window start in fast mode)
     const int* kL; const int* iL; const double* L; const double* diag; const int* mark;
     const int* rowptr; const int* rk; const int* rj;   // ascending row lists
     const int* parent;
@@ -325,7 +348,7 @@ static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArg
         int r = 0;
         if (lane == 0) r = atomicAdd(&a.counters[C_NEXT], 1);
         r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= a.N) break;
+        if (r >= a.nclaim) break;
         double acc = a.z[r];                         // right-hand side entry, written before the launch
         const int rb = a.rowptr[r], re = a.rowptr[r + 1];
         for (int t0 = rb; t0 < re; t0 += 32) {
@@ -364,10 +387,10 @@ static __global__ void __launch_bounds__(kSolveThreads) k_bwd_flags(FlagSolveArg
         int c = 0;
         if (lane == 0) c = atomicAdd(&a.counters[C_NEXT], 1);
         c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= a.N) break;
-        const int i = a.N - 1 - c;
+        if (c >= a.nclaim) break;
+        const int i = a.nclaim - 1 - c;
         const int par = a.parent[i];
-        if (lane == 0 && par >= 0) {
+        if (lane == 0 && par >= 0 && par < a.nclaim) {   // columns >= nclaim were solved before this launch
             while (vbk_ld_volatile(&a.done[par]) == 0) __nanosleep(20);
             __threadfence();
         }

@@ -1,0 +1,327 @@
+// vbk_fast.cuh -- FAST arithmetic mode: the trailing dense window of L as a dense problem.
+//
+// In the reference's ordering the last W columns of L are completely full (the "dense window",
+// ldlt.c:1027; W = 239 / 695 / 2766 for 25fv47 / pilot87 / dfl001) and hold half or more of the
+// factorisation's flops, but the reference's left-looking order makes them one dependent chain of W
+// columns.  Fast mode gives up that order (so results agree with the reference to rounding, not bit
+// for bit) and treats the window as what it is:
+//   1. the sparse columns j < T are factorised by the task kernel of vbk_factor_tiled.cuh;
+//   2. the same kernel in "phase 2" assembles the Schur complement of those columns into a dense
+//      W x W scratch matrix (no dependencies: every task can run at once);
+//   3. a blocked right-looking dense LDL^T (panel width <= 32: diagonal block, row-parallel TRSM,
+//      tiled rank-nb update with explicit FP64 FMAs) factorises the scratch matrix;
+//   4. triangular solves use dense panel sweeps on the window and the flag kernels below it.
+// The exact-zero pivot rule of the reference (ldlt.c:600-614) is kept bit-exact in the sparse part;
+// inside the window, where sums are re-associated, "exactly zero" becomes |d| <= tol * (sum of the
+// magnitudes of the terms that formed d) (option ii).
+#pragma once
+#include "vbk_factor_tiled.cuh"
+
+namespace vbk {
+
+constexpr int kPanelMax = 32;
+#ifdef VBK_EMU
+constexpr int kDenseThreads = 32;
+constexpr int kTileDim = 8;       // trailing-update tile edge in the emulated build
+#else
+constexpr int kDenseThreads = 256;
+constexpr int kTileDim = 64;
+#endif
+
+struct DenseArgs {
+    int W, ld, p, nb;          // window size, leading dimension, panel start, panel width
+    double* S;                 // dense scratch, column-major; lower triangle + diagonal
+    double* P;                 // panel scratch W x kPanelMax (ld = W): L21 * D of the current panel
+    double* dvec; double* wmag; int* wmark;
+    double* pan_d; int* pan_keep;      // [kPanelMax] pivots / marks of the current panel
+    const int* perm; int T, n_ld;
+    int* counters;
+    double tol;
+};
+
+__device__ __forceinline__ double& SW(const DenseArgs& a, int r, int c) { return a.S[(size_t)r + (size_t)c * a.ld]; }
+
+// A1: factor the nb x nb diagonal block (one CTA).  Unblocked LDL^T in shared memory.
+static __global__ void __launch_bounds__(kDenseThreads) k_dense_diag(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* blk = reinterpret_cast<double*>(raw);            // [nb][kPanelMax+1]
+    double* sd = blk + kPanelMax * (kPanelMax + 1);          // [kPanelMax] pivots
+    double* red = sd + kPanelMax;                            // [kDenseThreads]
+    int* skeep = reinterpret_cast<int*>(red + kDenseThreads); // [kPanelMax]
+    const int tid = threadIdx.x, nt = blockDim.x, nb = a.nb, p = a.p;
+    const int LDB = kPanelMax + 1;
+    for (int e = tid; e < nb * nb; e += nt) {
+        int r = e % nb, c = e / nb;
+        blk[r * LDB + c] = (r >= c) ? SW(a, p + r, p + c) : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < nb; ++c) {
+        double d = blk[c * LDB + c];
+        int keep = 1;
+        const bool dep = fabs(d) <= a.tol * a.wmag[p + c];
+        if (dep) {
+            // rare path (ldlt.c:600-614): max |updated column below the pivot|.  Rows inside the block
+            // are up to date; rows below the block get the panel's earlier columns applied on the fly.
+            double mymax = 0.0;
+            for (int r = c + 1 + tid; r < a.W - p; r += nt) {
+                double v;
+                if (r < nb) v = blk[r * LDB + c];
+                else {
+                    double l[kPanelMax];
+                    for (int c1 = 0; c1 < c; ++c1) {
+                        double s = SW(a, p + r, p + c1);
+                        for (int c0 = 0; c0 < c1; ++c0) s = fma(-l[c0] * sd[c0], blk[c1 * LDB + c0], s);
+                        l[c1] = skeep[c1] ? s / sd[c1] : 0.0;
+                    }
+                    v = SW(a, p + r, p + c);
+                    for (int c0 = 0; c0 < c; ++c0) v = fma(-l[c0] * sd[c0], blk[c * LDB + c0], v);
+                }
+                if (fabs(v) > mymax) mymax = fabs(v);
+            }
+            red[tid] = mymax;
+            __syncthreads();
+            if (tid == 0) {
+                double m = 0.0;
+                for (int u = 0; u < nt; ++u) if (red[u] > m) m = red[u];
+                red[0] = m;
+            }
+            __syncthreads();
+            if (red[0] < 1.0e+6 * 1.0e-8) keep = 0;
+            else d = (a.perm[a.T + p + c] < a.n_ld ? -1 : 1) * 1.0e-8;
+            if (tid == 0) atomicAdd(&a.counters[C_NDEP], 1);
+            __syncthreads();
+        }
+        if (tid == 0) { sd[c] = d; skeep[c] = keep; blk[c * LDB + c] = d; }
+        // column c of L inside the block, then the trailing part of the block
+        for (int r = c + 1 + tid; r < nb; r += nt) blk[r * LDB + c] = keep ? blk[r * LDB + c] / d : 0.0;
+        __syncthreads();
+        if (keep) {
+            const int rem = nb - c - 1;
+            for (int e = tid; e < rem * rem; e += nt) {
+                int r = c + 1 + e % rem, c2 = c + 1 + e / rem;
+                if (r >= c2) {
+                    double upd = blk[r * LDB + c] * d * blk[c2 * LDB + c];
+                    blk[r * LDB + c2] -= upd;
+                    if (r == c2 && fabs(upd) > a.wmag[p + r]) a.wmag[p + r] = fabs(upd);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nb * nb; e += nt) {
+        int r = e % nb, c = e / nb;
+        if (r > c) SW(a, p + r, p + c) = blk[r * LDB + c];
+    }
+    if (tid < nb) {
+        a.dvec[p + tid] = sd[tid];
+        a.wmark[p + tid] = skeep[tid];
+        a.pan_d[tid] = sd[tid];
+        a.pan_keep[tid] = skeep[tid];
+    }
+}
+
+// A2: rows below the block: L21 = S21 * L11^{-T} * D11^{-1}, one thread per row; also P = L21*D11 and
+// the diagonal of the trailing matrix (with its term magnitudes).
+static __global__ void __launch_bounds__(kDenseThreads) k_dense_trsm(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* l11 = reinterpret_cast<double*>(raw);            // [nb][kPanelMax+1]
+    double* sd = l11 + kPanelMax * (kPanelMax + 1);
+    int* skeep = reinterpret_cast<int*>(sd + kPanelMax);
+    const int tid = threadIdx.x, nt = blockDim.x, nb = a.nb, p = a.p;
+    const int LDB = kPanelMax + 1;
+    for (int e = tid; e < nb * nb; e += nt) {
+        int r = e % nb, c = e / nb;
+        l11[r * LDB + c] = (r > c) ? SW(a, p + r, p + c) : 0.0;
+    }
+    if (tid < nb) { sd[tid] = a.pan_d[tid]; skeep[tid] = a.pan_keep[tid]; }
+    __syncthreads();
+    for (int r = p + nb + blockIdx.x * nt + tid; r < a.W; r += gridDim.x * nt) {
+        double l[kPanelMax];
+        double dsum = 0.0, dabs = 0.0;
+        for (int c = 0; c < nb; ++c) {
+            double s = SW(a, r, p + c);
+            for (int c0 = 0; c0 < c; ++c0) s = fma(-l[c0] * sd[c0], l11[c * LDB + c0], s);
+            l[c] = skeep[c] ? s / sd[c] : 0.0;
+        }
+        for (int c = 0; c < nb; ++c) {
+            const double w = l[c] * sd[c];
+            SW(a, r, p + c) = l[c];
+            a.P[(size_t)r + (size_t)c * a.W] = w;
+            const double t = l[c] * w;
+            dsum += t;
+            if (fabs(t) > dabs) dabs = fabs(t);
+        }
+        SW(a, r, r) -= dsum;
+        if (dabs > a.wmag[r]) a.wmag[r] = dabs;
+    }
+}
+
+// A3: strictly-lower trailing update  S[r,c2] -= sum_c L21[r,c] * P[c2,c]  in square tiles.
+static __global__ void __launch_bounds__(kDenseThreads) k_dense_update(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* As = reinterpret_cast<double*>(raw);             // [nb][kTileDim]   L21 rows of this tile
+    double* Bs = As + kPanelMax * kTileDim;                  // [nb][kTileDim]   P rows of this tile's columns
+    const int tr = blockIdx.y, tc = blockIdx.x;
+    if (tr < tc) return;
+    const int base = a.p + a.nb, nb = a.nb;
+    const int r0 = base + tr * kTileDim, c0 = base + tc * kTileDim;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < nb * kTileDim; e += nt) {
+        int x = e % kTileDim, c = e / kTileDim;
+        As[c * kTileDim + x] = (r0 + x < a.W) ? SW(a, r0 + x, a.p + c) : 0.0;
+        Bs[c * kTileDim + x] = (c0 + x < a.W) ? a.P[(size_t)(c0 + x) + (size_t)c * a.W] : 0.0;
+    }
+    __syncthreads();
+    // each thread: a strip of the tile, 4 rows x (kTileDim*kTileDim/(4*nt)) columns
+    // each work item: RPT rows (interleaved by `rgroups`, so a warp touches consecutive rows of one
+    // column = coalesced) of one tile column
+    constexpr int RPT = 4;
+    const int rgroups = kTileDim / RPT;
+    for (int item = tid; item < rgroups * kTileDim; item += nt) {
+        const int rg = item % rgroups, cc = item / rgroups;
+        double acc[RPT] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = 0; c < nb; ++c) {
+            const double b = Bs[c * kTileDim + cc];
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) acc[u] = fma(As[c * kTileDim + u * rgroups + rg], b, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int r = r0 + u * rgroups + rg, c2 = c0 + cc;
+            if (r < a.W && c2 < a.W && r > c2) SW(a, r, c2) -= acc[u];
+        }
+    }
+}
+
+// copy the factored window back into the packed storage of L, diag and mark
+static __global__ void k_window_store(int W, int T, int ld, const double* __restrict__ S, const double* __restrict__ dvec,
+                                      const int* __restrict__ wmark, const int* __restrict__ kL,
+                                      double* __restrict__ L, double* __restrict__ diag, int* __restrict__ mark)
+{
+    for (int c = blockIdx.y; c < W; c += gridDim.y) {
+        const int base = kL[T + c];
+        for (int r = c + 1 + blockIdx.x * blockDim.x + threadIdx.x; r < W; r += gridDim.x * blockDim.x)
+            L[base + (r - c - 1)] = S[(size_t)r + (size_t)c * ld];
+        if (blockIdx.x == 0 && threadIdx.x == 0) { diag[T + c] = dvec[c]; if (!wmark[c]) mark[T + c] = 0; }
+    }
+}
+
+static __global__ void k_zero_counter(int* counters, int slot) { if (threadIdx.x == 0 && blockIdx.x == 0) counters[slot] = 0; }
+
+// --------------------------------------------------------------------------------------------
+// Fast-mode triangular solves on the window (rows/columns T..N-1, unit-lower L packed in `L`).
+// Packed layout: column T+c starts at kL[T+c] and holds rows T+c+1..N-1 contiguously.
+// --------------------------------------------------------------------------------------------
+struct WindowSolveArgs {
+    int N, T;
+    const int* kL; const double* L; const int* mark;
+    const int* rowptr; const int* rk; const int* rj;     // ascending row lists (for the coupling rows)
+    double* z;
+    int* counters; const unsigned long long* scal_bits; double epssol;
+};
+__device__ __forceinline__ double win_eps(const WindowSolveArgs& a) {
+    return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;
+}
+__device__ __forceinline__ double WL(const WindowSolveArgs& a, int r, int c) {   // L[T+r, T+c], r > c
+    return a.L[a.kL[a.T + c] + (r - c - 1)];
+}
+
+// z[r] -= sum_{j<T} L[r,j] z[j] for window rows r (the sparse columns' contribution), warp per row
+static __global__ void __launch_bounds__(kSolveThreads) k_window_gather(WindowSolveArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = a.T + warp; r < a.N; r += nwarps) {
+        double s = 0.0;
+        for (int t = a.rowptr[r] + lane; t < a.rowptr[r + 1]; t += 32) {
+            const int j = a.rj[t];
+            if (j < a.T && a.mark[j]) s = fma(a.L[a.rk[t]], a.z[j], s);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) a.z[r] -= s;
+    }
+}
+
+// forward sweep on the window: one CTA, 32-column panels
+static __global__ void __launch_bounds__(kDenseThreads) k_window_fwd(WindowSolveArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* zp = reinterpret_cast<double*>(raw);      // [32] finished panel entries
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, W = a.N - a.T;
+    const double eps = win_eps(a);
+    double* z = a.z + a.T;
+    for (int p = 0; p < W; p += 32) {
+        const int nb = (W - p < 32) ? (W - p) : 32;
+        if (tid < 32) {
+            double v = (lane < nb) ? z[p + lane] : 0.0;
+            double lrow[32];                                    // this lane's row of the diagonal block
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                lrow[c] = (c < lane && lane < nb && a.mark[a.T + p + c]) ? WL(a, p + lane, p + c) : 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                double zc = __shfl_sync(0xffffffffu, v, c);
+                if (c < nb && lane == c && !a.mark[a.T + p + c]) {   // rawsolve's unmarked-row rule
+                    if (fabs(v) > eps) a.counters[C_CONSISTENT] = 0; else v = 0.0;
+                }
+                if (lrow[c] != 0.0) v = fma(-lrow[c], zc, v);   // lrow[c] == 0 where nothing applies
+            }
+            if (lane < nb) { z[p + lane] = v; zp[lane] = a.mark[a.T + p + lane] ? v : 0.0; }
+        }
+        __syncthreads();
+        for (int r = p + nb + tid; r < W; r += nt) {
+            double acc = z[r];
+            for (int c = 0; c < nb; ++c) acc = fma(-WL(a, r, p + c), zp[c], acc);
+            z[r] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// backward sweep on the window (L^T): one CTA; each warp reduces one panel column's tail product
+static __global__ void __launch_bounds__(kDenseThreads) k_window_bwd(WindowSolveArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* part = reinterpret_cast<double*>(raw);    // [32]
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int W = a.N - a.T;
+    const double eps = win_eps(a);
+    double* z = a.z + a.T;
+    const int npanels = (W + 31) / 32;
+    for (int pi = npanels - 1; pi >= 0; --pi) {
+        const int p = pi * 32;
+        const int nb = (W - p < 32) ? (W - p) : 32;
+        for (int c = warp; c < nb; c += nwarps) {
+            double s = 0.0;
+            if (a.mark[a.T + p + c])
+                for (int r = p + nb + lane; r < W; r += 32) s = fma(WL(a, r, p + c), z[r], s);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == 0) part[c] = s;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double v = (lane < nb) ? z[p + lane] - part[lane] : 0.0;
+            double lcol[32];                                    // this lane's column of the diagonal block
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                lcol[c] = (c > lane && c < nb && a.mark[a.T + p + lane]) ? WL(a, p + c, p + lane) : 0.0;
+#pragma unroll
+            for (int c = 31; c >= 0; --c) {
+                if (c < nb && lane == c && !a.mark[a.T + p + c]) {
+                    if (fabs(v) > eps) a.counters[C_CONSISTENT] = 0; else v = 0.0;
+                }
+                double zc = __shfl_sync(0xffffffffu, v, c);
+                if (lcol[c] != 0.0) v = fma(-lcol[c], zc, v);
+            }
+            if (lane < nb) z[p + lane] = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace vbk

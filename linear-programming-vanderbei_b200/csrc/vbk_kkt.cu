@@ -195,6 +195,7 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
         tiled_grid_ = (int)g2;
         if ((size_t)tiled_grid_ > (size_t)factor_grid_) slotmap_.alloc((size_t)tiled_grid_ * N);
     }
+    if (mode_ == kFast) prepare_fast();
     VBK_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -256,20 +257,13 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
         VBK_LAUNCH(k_tiled_reset, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, col_ntask_.p, pend_.p,
                    col_left_.p, col_ready_.p, piv_flag_.p, counters_.p);
         TiledArgs ta;
-        ta.N = N; ta.n_ld = n; ta.ntasks = sym_.ntasks(); ta.tile_doubles = tile_doubles_; ta.temp_cap = temp_cap_;
-        ta.kL = kL_.p; ta.iL = iL_.p; ta.L = L_.p; ta.diag = diag_.p; ta.mark = mark_.p;
-        ta.rowptr = rowptr_.p; ta.rk = rk_sig_.p; ta.rj = rj_sig_.p;
-        ta.parent = parent_.p; ta.perm = perm_.p;
-        ta.task_col = task_col_.p; ta.task_blk = task_blk_.p; ta.task_pos0 = task_pos0_.p; ta.task_cnt = task_cnt_.p;
-        ta.col_task0 = col_task0_.p; ta.col_ntask = col_ntask_.p;
-        ta.winptr = winptr_.p; ta.nblk = sym_.nblk; ta.rowblk = sym_.rowblk; ta.slice_row0 = sym_.slice_row0;
-        ta.pend = pend_.p; ta.col_left = col_left_.p; ta.col_ready = col_ready_.p; ta.piv_flag = piv_flag_.p;
-        ta.piv_val = piv_val_.p; ta.piv_keep = piv_keep_.p; ta.task_max = task_max_.p;
-        ta.counters = counters_.p; ta.scal_bits = bits_.p; ta.epsnum = 0.0;       // _EPSNUM, ldlt.c:29
-        ta.slotmap = slotmap_.p;
-        ta.prof = prof_.p;
+        fill_tiled_args(ta);
         VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
-        VBK_LAUNCH(k_factor_tiled, tiled_grid_, kTiledThreads, tiled_smem_, stream_, ta);
+        if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
+            factor_window_fast(ta);               // sparse part + Schur assembly + dense window (vbk_kkt_fast.cu)
+        } else {
+            VBK_LAUNCH(k_factor_tiled, tiled_grid_, kTiledThreads, tiled_smem_, stream_, ta);
+        }
         VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
         VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);
         VBK_LAUNCH(k_update_epsdiag, 1, 32, 0, stream_, scal_.p, bits_.p);
@@ -299,6 +293,23 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
     stats.kernel_launches += 9;
 }
 
+void Kkt::fill_tiled_args(TiledArgs& ta)
+{
+    ta.N = sym_.N; ta.n_ld = sym_.n; ta.ntasks = sym_.ntasks(); ta.tile_doubles = tile_doubles_; ta.temp_cap = temp_cap_;
+    ta.kL = kL_.p; ta.iL = iL_.p; ta.L = L_.p; ta.diag = diag_.p; ta.mark = mark_.p;
+    ta.rowptr = rowptr_.p; ta.rk = rk_sig_.p; ta.rj = rj_sig_.p;
+    ta.parent = parent_.p; ta.perm = perm_.p;
+    ta.task_col = task_col_.p; ta.task_blk = task_blk_.p; ta.task_pos0 = task_pos0_.p; ta.task_cnt = task_cnt_.p;
+    ta.col_task0 = col_task0_.p; ta.col_ntask = col_ntask_.p;
+    ta.winptr = winptr_.p; ta.nblk = sym_.nblk; ta.rowblk = sym_.rowblk; ta.slice_row0 = sym_.slice_row0;
+    ta.pend = pend_.p; ta.col_left = col_left_.p; ta.col_ready = col_ready_.p; ta.piv_flag = piv_flag_.p;
+    ta.piv_val = piv_val_.p; ta.piv_keep = piv_keep_.p; ta.task_max = task_max_.p;
+    ta.counters = counters_.p; ta.scal_bits = bits_.p; ta.epsnum = 0.0;       // _EPSNUM, ldlt.c:29
+    ta.slotmap = slotmap_.p;
+    ta.prof = prof_.p;
+    ta.phase = 0; ta.task_base = 0; ta.T = sym_.N; ta.ldw = 0; ta.Sw = nullptr; ta.wmag = nullptr;
+}
+
 void Kkt::rawsolve_dev()
 {
     require_device("rawsolve");
@@ -320,7 +331,12 @@ void Kkt::rawsolve_dev()
         fs.N = N; fs.kL = kL_.p; fs.iL = iL_.p; fs.L = L_.p; fs.diag = diag_.p; fs.mark = mark_.p;
         fs.rowptr = rowptr_.p; fs.rk = rk_asc_.p; fs.rj = rj_asc_.p; fs.parent = parent_.p;
         fs.z = z_.p; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
+        fs.nclaim = N;
         const size_t sm = (size_t)(kSolveThreads / 32) * 128 * sizeof(double);
+        if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
+            rawsolve_window_fast(fs, sa, sm);     // flag kernels below the window, dense sweeps on it
+            return;
+        }
         VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
         VBK_LAUNCH(k_fwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
         VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);

@@ -12,6 +12,9 @@
 namespace vbk {
 
 enum Mode { kStrict = 0, kFast = 1 };
+struct TiledArgs;
+struct FlagSolveArgs;
+struct SolveArgs;
 
 // owning device array
 template <class T>
@@ -134,6 +137,16 @@ private:
     DevArray<unsigned long long> prof_;   // $VBK_PROF: per-phase cycle counters of the tiled factor kernel
     int tiled_grid_ = 1, tile_doubles_ = 8192, temp_cap_ = 512;
     size_t tiled_smem_ = 0;
+    void fill_tiled_args(TiledArgs& ta);
+
+    // fast mode (vbk_fast.cuh, vbk_kkt_fast.cu): dense scratch for the trailing window
+    bool fast_ready_ = false;
+    int panel_nb_ = 32;
+    DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_;
+    DevArray<int> wmark_, pan_keep_;
+    void prepare_fast();
+    void factor_window_fast(TiledArgs& ta);
+    void rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_smem);
     int factor_grid_ = 1, solve_grid_ = 1;
     cudaEvent_t ev_f0_ = nullptr, ev_f1_ = nullptr;
     size_t factor_smem_ = 0;

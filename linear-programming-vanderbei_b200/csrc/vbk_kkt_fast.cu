@@ -1,0 +1,107 @@
+// vbk_kkt_fast.cu -- host orchestration of FAST mode (kernels in vbk_fast.cuh).
+#include "vbk_kkt.h"
+#include "vbk_fast.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+namespace vbk {
+
+void Kkt::prepare_fast()
+{
+    const int N = sym_.N, T = sym_.dense_start, W = N - T;
+    fast_ready_ = false;
+    if (W <= 0) return;
+    if (const char* e = std::getenv("VBK_PANEL")) panel_nb_ = std::max(1, std::min(kPanelMax, std::atoi(e)));
+    else panel_nb_ = kPanelMax;
+    Sw_.alloc((size_t)W * W);
+    P_.alloc((size_t)W * kPanelMax);
+    dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
+    pan_d_.alloc(kPanelMax); pan_keep_.alloc(kPanelMax);
+#ifndef VBK_EMU
+    // kernels are `static` in the headers: this translation unit launches its own copy
+    VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_));
+#endif
+    fast_ready_ = true;
+}
+
+// Numeric factorisation in fast mode.  `ta` arrives filled for a plain (phase 0) launch.
+void Kkt::factor_window_fast(TiledArgs& ta)
+{
+    const int N = sym_.N, T = sym_.dense_start, W = N - T;
+    const int sparse_tasks = sym_.col_task0[T];
+
+    // 1. columns j < T: the strict task kernel (bit-exact for these columns, dependent-pivot rule
+    //    included).  k_tiled_reset has already run.
+    if (sparse_tasks > 0) {
+        ta.phase = 0; ta.task_base = 0; ta.ntasks = sparse_tasks;
+        VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(sparse_tasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
+    }
+    // 2. Schur complement of the sparse columns on the window, written densely; no dependencies
+    VBK_LAUNCH(k_zero_counter, 1, 32, 0, stream_, counters_.p, (int)C_NEXT);
+    ta.phase = 2; ta.task_base = sparse_tasks; ta.ntasks = sym_.ntasks() - sparse_tasks;
+    ta.T = T; ta.ldw = W; ta.Sw = Sw_.p; ta.wmag = wmag_.p;
+    VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(ta.ntasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
+
+    // 3. blocked right-looking dense LDL^T of the window
+    DenseArgs da;
+    da.W = W; da.ld = W; da.S = Sw_.p; da.P = P_.p; da.dvec = dvec_.p; da.wmag = wmag_.p; da.wmark = wmark_.p;
+    da.pan_d = pan_d_.p; da.pan_keep = pan_keep_.p; da.perm = perm_.p; da.T = T; da.n_ld = sym_.n;
+    da.counters = counters_.p;
+    // The reference's "exactly zero" pivots come from absorption: a term T swallows the running value
+    // (|value| < ulp(T)/2) and is then cancelled exactly.  With re-associated sums the same pivot comes
+    // out as the tiny true value instead, so the test is |d| <= 2^-52 * (largest term magnitude).
+    da.tol = 2.220446049250313e-16;
+    const size_t sm_diag = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax + kDenseThreads) + sizeof(int) * kPanelMax;
+    const size_t sm_trsm = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;
+    const size_t sm_upd = sizeof(double) * 2 * kPanelMax * kTileDim;
+    int launches = 2;
+    for (int p = 0; p < W; p += panel_nb_) {
+        da.p = p; da.nb = std::min(panel_nb_, W - p);
+        VBK_LAUNCH(k_dense_diag, 1, kDenseThreads, sm_diag, stream_, da);
+        ++launches;
+        const int below = W - p - da.nb;
+        if (below > 0) {
+            const int g = std::min((below + kDenseThreads - 1) / kDenseThreads, num_sms_ * 4);
+            VBK_LAUNCH(k_dense_trsm, g, kDenseThreads, sm_trsm, stream_, da);
+            const int tiles = (below + kTileDim - 1) / kTileDim;
+            VBK_LAUNCH(k_dense_update, dim3(tiles, tiles), kDenseThreads, sm_upd, stream_, da);
+            launches += 2;
+        }
+    }
+    // 4. back into the packed storage the solves and the tests read
+    {
+        const int gx = std::max(1, std::min((W + kVecThreads - 1) / kVecThreads, 64));
+        const int gy = std::max(1, std::min(W, 1024));
+        VBK_LAUNCH(k_window_store, dim3(gx, gy), kVecThreads, 0, stream_, W, T, W, Sw_.p, dvec_.p, wmark_.p, kL_.p,
+                   L_.p, diag_.p, mark_.p);
+        ++launches;
+    }
+    stats.kernel_launches += launches;
+}
+
+void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_smem)
+{
+    const int N = sym_.N, T = sym_.dense_start;
+    WindowSolveArgs wa;
+    wa.N = N; wa.T = T; wa.kL = kL_.p; wa.L = L_.p; wa.mark = mark_.p;
+    wa.rowptr = rowptr_.p; wa.rk = rk_asc_.p; wa.rj = rj_asc_.p; wa.z = z_.p;
+    wa.counters = counters_.p; wa.scal_bits = bits_.p; wa.epssol = 1.0e-6;
+    fs.nclaim = T;
+    const int gsolve = std::max(1, std::min(solve_grid_, (T + 3) / 4));
+    const int ggather = std::max(1, std::min(num_sms_ * 4, ((N - T) * 32 + kSolveThreads - 1) / kSolveThreads));
+
+    VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
+    if (T > 0) VBK_LAUNCH(k_fwd_flags, gsolve, kSolveThreads, flag_smem, stream_, fs);
+    VBK_LAUNCH(k_window_gather, ggather, kSolveThreads, 0, stream_, wa);
+    VBK_LAUNCH(k_window_fwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
+    VBK_LAUNCH(k_window_bwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
+    if (T > 0) VBK_LAUNCH(k_bwd_flags, gsolve, kSolveThreads, flag_smem, stream_, fs);
+    VBK_CHECK_LAUNCH();
+    stats.kernel_launches += 10;
+}
+
+}  // namespace vbk

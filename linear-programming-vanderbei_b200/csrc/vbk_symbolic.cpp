@@ -341,6 +341,11 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
         col_ntask[j] = (int)task_col.size() - col_task0[j];
     }
 
+    dense_start = N;
+    for (int j = N - 1; j >= 0; --j) {
+        if (kL[j + 1] - kL[j] == N - 1 - j) dense_start = j; else break;
+    }
+
     // fundamental supernodes: column j+1 continues j's supernode when j+1 is j's only-child parent
     // and struct(j+1) = struct(j) \ {j+1}
     sn_ptr.clear();

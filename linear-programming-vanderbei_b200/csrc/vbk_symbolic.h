@@ -54,6 +54,9 @@ struct Symbolic {
     std::vector<int> task_col, task_blk, task_pos0, task_cnt;   // blk = -1: whole column
     std::vector<int> col_task0, col_ntask;                      // [N]
     int ntasks() const { return (int)task_col.size(); }
+    // first column of the trailing dense window: every column j >= dense_start holds all rows j+1..N-1
+    // (the reference's denwin, ldlt.c:1027, re-derived from the pattern so that it can be trusted)
+    int dense_start = 0;
 
     // fundamental supernodes: column ranges [sn_ptr[s], sn_ptr[s+1])
     std::vector<int> sn_ptr;

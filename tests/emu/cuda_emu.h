@@ -178,7 +178,7 @@ namespace emu {
 // Run `body` once per emulated CUDA thread.  All CTAs run concurrently (needed by the dataflow
 // kernels, whose CTAs wait on one another).
 inline void launch(dim3 g, dim3 b, size_t smem_bytes, const std::function<void()>& body) {
-    unsigned nthreads = b.x, nctas = g.x;
+    unsigned nthreads = b.x, nctas = g.x * g.y;
     Grid grid_state;
     grid_state.bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)nthreads * nctas);
     std::vector<Cta> ctas(nctas);
@@ -196,7 +196,7 @@ inline void launch(dim3 g, dim3 b, size_t smem_bytes, const std::function<void()
             pool.emplace_back([&, cb, t] {
                 cta = &ctas[cb];
                 grid = &grid_state;
-                threadIdx = dim3(t); blockIdx = dim3(cb); blockDim = b; gridDim = g;
+                threadIdx = dim3(t); blockIdx = dim3(cb % g.x, cb / g.x); blockDim = b; gridDim = g;
                 body();
             });
     for (auto& th : pool) th.join();
