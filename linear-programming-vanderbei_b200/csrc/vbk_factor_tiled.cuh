@@ -300,6 +300,7 @@ static __global__ void __launch_bounds__(kTiledThreads) k_factor_tiled(TiledArgs
 struct FlagSolveArgs {
     int N;
     int nclaim;   // rows [0, nclaim) forward / columns nclaim-1..0 backward (N, or the window start in fast mode)
+    int fast;     // 1: sums may be re-associated (tree reductions, FMA)
     const int* kL; const int* iL; const double* L; const double* diag; const int* mark;
     const int* rowptr; const int* rk; const int* rj;   // ascending row lists
     const int* parent;
@@ -397,7 +398,17 @@ static __global__ void __launch_bounds__(kSolveThreads) k_bwd_flags(FlagSolveArg
         __syncwarp();
         double beta = a.z[i];                        // z[i] after the diagonal sweep (previous launch)
         if (a.mark[i]) {
-            const int kb = a.kL[i], ke = a.kL[i + 1];
+            int kb = a.kL[i];
+            const int ke = a.kL[i + 1];
+            if (a.fast) {
+                // fast mode: the order of the sum is free -- per-lane partial sums, then a shuffle tree
+                double s = 0.0;
+                for (int k = kb + lane; k < ke; k += 32) s = fma(a.L[k], __ldcg(&a.z[a.iL[k]]), s);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                beta -= s;
+                kb = ke;          // nothing left for the ordered path below
+            }
             // 128 entries per round: the raw operands of the NEXT round are loaded before the dependent
             // subtract chain of the current one and multiplied only afterwards, so the two L2 round
             // trips (iL -> z) hide behind the chain instead of stalling it

@@ -196,15 +196,74 @@ static __global__ void __launch_bounds__(kDenseThreads) k_dense_update(DenseArgs
     }
 }
 
+// A3, register-tiled: TD x TD tiles, TG x TG threads, an 8 x 8 micro-tile per thread held in registers
+// (rows 2*tx+{0,1}+2*TG*u, columns 2*ty+{0,1}+2*TG*v: consecutive threads touch consecutive rows of a
+// column-major tile => coalesced C traffic and conflict-free 16-byte shared-memory reads).  64 FMAs per
+// 8 shared-memory loads of 16 bytes: the FP64 pipe, not the LSU, is the limiter.
+#ifdef VBK_EMU
+constexpr int kUpdTG = 4;
+#else
+constexpr int kUpdTG = 16;
+#endif
+constexpr int kUpdTD = 8 * kUpdTG;
+constexpr int kUpdThreads = kUpdTG * kUpdTG;
+
+static __global__ void __launch_bounds__(kUpdThreads) k_dense_update_rt(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* As = reinterpret_cast<double*>(raw);             // [nb][kUpdTD]
+    double* Bs = As + kPanelMax * kUpdTD;                    // [nb][kUpdTD]
+    const int tr = blockIdx.y, tc = blockIdx.x;
+    if (tr < tc) return;
+    const int base = a.p + a.nb, nb = a.nb;
+    const int r0 = base + tr * kUpdTD, c0 = base + tc * kUpdTD;
+    const int tid = threadIdx.x, tx = tid % kUpdTG, ty = tid / kUpdTG;
+    for (int e = tid; e < nb * kUpdTD; e += kUpdThreads) {
+        const int x = e % kUpdTD, c = e / kUpdTD;
+        As[c * kUpdTD + x] = (r0 + x < a.W) ? SW(a, r0 + x, a.p + c) : 0.0;
+        Bs[c * kUpdTD + x] = (c0 + x < a.W) ? a.P[(size_t)(c0 + x) + (size_t)c * a.W] : 0.0;
+    }
+    __syncthreads();
+    double acc[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[u][v] = 0.0;
+    for (int c = 0; c < nb; ++c) {
+        double av[8], bv[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            av[2 * u] = As[c * kUpdTD + 2 * tx + 2 * kUpdTG * u];
+            av[2 * u + 1] = As[c * kUpdTD + 2 * tx + 2 * kUpdTG * u + 1];
+            bv[2 * u] = Bs[c * kUpdTD + 2 * ty + 2 * kUpdTG * u];
+            bv[2 * u + 1] = Bs[c * kUpdTD + 2 * ty + 2 * kUpdTG * u + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const int c2 = c0 + 2 * ty + 2 * kUpdTG * (v >> 1) + (v & 1);
+        if (c2 >= a.W) continue;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = r0 + 2 * tx + 2 * kUpdTG * (u >> 1) + (u & 1);
+            if (r < a.W && r > c2) SW(a, r, c2) -= acc[u][v];
+        }
+    }
+}
+
 // copy the factored window back into the packed storage of L, diag and mark
 static __global__ void k_window_store(int W, int T, int ld, const double* __restrict__ S, const double* __restrict__ dvec,
-                                      const int* __restrict__ wmark, const int* __restrict__ kL,
+                                      const int* __restrict__ wmark, const int* __restrict__ kL, const int* __restrict__ iL,
                                       double* __restrict__ L, double* __restrict__ diag, int* __restrict__ mark)
 {
     for (int c = blockIdx.y; c < W; c += gridDim.y) {
-        const int base = kL[T + c];
-        for (int r = c + 1 + blockIdx.x * blockDim.x + threadIdx.x; r < W; r += gridDim.x * blockDim.x)
-            L[base + (r - c - 1)] = S[(size_t)r + (size_t)c * ld];
+        const int kb = kL[T + c], ke = kL[T + c + 1];       // only the entries of the fill pattern exist in L
+        for (int k = kb + blockIdx.x * blockDim.x + threadIdx.x; k < ke; k += gridDim.x * blockDim.x)
+            L[k] = S[(size_t)(iL[k] - T) + (size_t)c * ld];
         if (blockIdx.x == 0 && threadIdx.x == 0) { diag[T + c] = dvec[c]; if (!wmark[c]) mark[T + c] = 0; }
     }
 }
@@ -212,11 +271,13 @@ static __global__ void k_window_store(int W, int T, int ld, const double* __rest
 static __global__ void k_zero_counter(int* counters, int slot) { if (threadIdx.x == 0 && blockIdx.x == 0) counters[slot] = 0; }
 
 // --------------------------------------------------------------------------------------------
-// Fast-mode triangular solves on the window (rows/columns T..N-1, unit-lower L packed in `L`).
-// Packed layout: column T+c starts at kL[T+c] and holds rows T+c+1..N-1 contiguously.
+// Fast-mode triangular solves on the window (rows/columns T..N-1).  The unit-lower factor of the
+// window is read from the dense scratch S (column-major, leading dimension ld; zero outside the
+// fill pattern), which stays valid until the next factorisation.
 // --------------------------------------------------------------------------------------------
 struct WindowSolveArgs {
-    int N, T;
+    int N, T, ld;
+    const double* S;
     const int* kL; const double* L; const int* mark;
     const int* rowptr; const int* rk; const int* rj;     // ascending row lists (for the coupling rows)
     double* z;
@@ -226,7 +287,7 @@ __device__ __forceinline__ double win_eps(const WindowSolveArgs& a) {
     return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;
 }
 __device__ __forceinline__ double WL(const WindowSolveArgs& a, int r, int c) {   // L[T+r, T+c], r > c
-    return a.L[a.kL[a.T + c] + (r - c - 1)];
+    return a.S[(size_t)r + (size_t)c * a.ld];
 }
 
 // z[r] -= sum_{j<T} L[r,j] z[j] for window rows r (the sparse columns' contribution), warp per row

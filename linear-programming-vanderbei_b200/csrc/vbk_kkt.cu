@@ -332,6 +332,7 @@ void Kkt::rawsolve_dev()
         fs.rowptr = rowptr_.p; fs.rk = rk_asc_.p; fs.rj = rj_asc_.p; fs.parent = parent_.p;
         fs.z = z_.p; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
         fs.nclaim = N;
+        fs.fast = 0;
         const size_t sm = (size_t)(kSolveThreads / 32) * 128 * sizeof(double);
         if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
             rawsolve_window_fast(fs, sa, sm);     // flag kernels below the window, dense sweeps on it

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 namespace vbk {
 
@@ -22,6 +23,8 @@ void Kkt::prepare_fast()
 #ifndef VBK_EMU
     // kernels are `static` in the headers: this translation unit launches its own copy
     VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_rt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
 #endif
     fast_ready_ = true;
 }
@@ -38,7 +41,9 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         ta.phase = 0; ta.task_base = 0; ta.ntasks = sparse_tasks;
         VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(sparse_tasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
     }
-    // 2. Schur complement of the sparse columns on the window, written densely; no dependencies
+    // 2. Schur complement of the sparse columns on the window, written densely; no dependencies.
+    //    Entries outside the fill pattern are never written: start from zero.
+    VBK_CUDA(cudaMemsetAsync(Sw_.p, 0, sizeof(double) * (size_t)W * W, stream_));
     VBK_LAUNCH(k_zero_counter, 1, 32, 0, stream_, counters_.p, (int)C_NEXT);
     ta.phase = 2; ta.task_base = sparse_tasks; ta.ntasks = sym_.ntasks() - sparse_tasks;
     ta.T = T; ta.ldw = W; ta.Sw = Sw_.p; ta.wmag = wmag_.p;
@@ -56,6 +61,9 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     const size_t sm_diag = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax + kDenseThreads) + sizeof(int) * kPanelMax;
     const size_t sm_trsm = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;
     const size_t sm_upd = sizeof(double) * 2 * kPanelMax * kTileDim;
+    const size_t sm_upd_rt = sizeof(double) * 2 * kPanelMax * kUpdTD;
+    const char* eu = std::getenv("VBK_UPDATE");
+    const bool simple_update = eu && std::string(eu) == "simple";
     int launches = 2;
     for (int p = 0; p < W; p += panel_nb_) {
         da.p = p; da.nb = std::min(panel_nb_, W - p);
@@ -65,8 +73,13 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         if (below > 0) {
             const int g = std::min((below + kDenseThreads - 1) / kDenseThreads, num_sms_ * 4);
             VBK_LAUNCH(k_dense_trsm, g, kDenseThreads, sm_trsm, stream_, da);
-            const int tiles = (below + kTileDim - 1) / kTileDim;
-            VBK_LAUNCH(k_dense_update, dim3(tiles, tiles), kDenseThreads, sm_upd, stream_, da);
+            if (simple_update) {
+                const int tiles = (below + kTileDim - 1) / kTileDim;
+                VBK_LAUNCH(k_dense_update, dim3(tiles, tiles), kDenseThreads, sm_upd, stream_, da);
+            } else {
+                const int tiles = (below + kUpdTD - 1) / kUpdTD;
+                VBK_LAUNCH(k_dense_update_rt, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
+            }
             launches += 2;
         }
     }
@@ -75,7 +88,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         const int gx = std::max(1, std::min((W + kVecThreads - 1) / kVecThreads, 64));
         const int gy = std::max(1, std::min(W, 1024));
         VBK_LAUNCH(k_window_store, dim3(gx, gy), kVecThreads, 0, stream_, W, T, W, Sw_.p, dvec_.p, wmark_.p, kL_.p,
-                   L_.p, diag_.p, mark_.p);
+                   iL_.p, L_.p, diag_.p, mark_.p);
         ++launches;
     }
     stats.kernel_launches += launches;
@@ -85,10 +98,11 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
 {
     const int N = sym_.N, T = sym_.dense_start;
     WindowSolveArgs wa;
-    wa.N = N; wa.T = T; wa.kL = kL_.p; wa.L = L_.p; wa.mark = mark_.p;
+    wa.N = N; wa.T = T; wa.ld = N - T; wa.S = Sw_.p; wa.kL = kL_.p; wa.L = L_.p; wa.mark = mark_.p;
     wa.rowptr = rowptr_.p; wa.rk = rk_asc_.p; wa.rj = rj_asc_.p; wa.z = z_.p;
     wa.counters = counters_.p; wa.scal_bits = bits_.p; wa.epssol = 1.0e-6;
     fs.nclaim = T;
+    fs.fast = 1;
     const int gsolve = std::max(1, std::min(solve_grid_, (T + 3) / 4));
     const int ggather = std::max(1, std::min(num_sms_ * 4, ((N - T) * 32 + kSolveThreads - 1) / kSolveThreads));
 

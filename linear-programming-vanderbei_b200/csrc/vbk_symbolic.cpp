@@ -341,9 +341,23 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
         col_ntask[j] = (int)task_col.size() - col_task0[j];
     }
 
-    dense_start = N;
-    for (int j = N - 1; j >= 0; --j) {
-        if (kL[j + 1] - kL[j] == N - 1 - j) dense_start = j; else break;
+    // Trailing window treated densely by fast mode.  rho = 1 gives the reference's dense window
+    // (every column full); smaller rho admits columns that hold at least rho of the rows below them.
+    // Padding is exact: the fill pattern is closed under elimination, so entries outside it receive
+    // no contribution and stay 0.  The window is limited by memory (W^2 doubles <= 4 GiB) and by
+    // work (dense flops W^3/3 at most 8x the factorisation's own flop count).
+    {
+        double rho = 0.25;
+        if (const char* e = std::getenv("VBK_WINDOW_RHO")) rho = std::atof(e);
+        for (;;) {
+            dense_start = N;
+            for (int j = N - 1; j >= 0; --j) {
+                if ((double)(kL[j + 1] - kL[j]) >= rho * (double)(N - 1 - j)) dense_start = j; else break;
+            }
+            const double W = (double)(N - dense_start);
+            if (rho >= 1.0 || (W * W * 8.0 <= 4.0 * 1073741824.0 && W * W * W / 3.0 <= 8.0 * narth + 1.0e6)) break;
+            rho = std::min(1.0, rho * 2.0);
+        }
     }
 
     // fundamental supernodes: column j+1 continues j's supernode when j+1 is j's only-child parent

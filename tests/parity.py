@@ -78,6 +78,49 @@ def check_kkt_step(vbkkt, lib, oracle, lp, method, it, refine_rhs=True):
         K.close()
 
 
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def check_kkt_step_fast(vbkkt, lib, oracle, lp, method, it, tol=1e-6):
+    """FAST mode (re-associated sums, dense-window factorisation) on a captured iterate WITHOUT
+    dependent pivots: the factor and the refined solution agree with the oracle to rounding, and the
+    residual of K z = rhs is as small as the reference's own refinement criterion asks."""
+    import scipy.sparse as sp
+    E, D, ry, rx, sy, sx = H.capture_step(oracle, lp, method, it)
+    F = H.oracle_factor_for(oracle, lp)
+    K = H.kkt_for(vbkkt, lib, lp, mode=vbkkt.MODE_FAST)
+    try:
+        F.factor(E, D)
+        K.factor(E, D)
+        assert F.ndep == 0, "pick an iterate without dependent pivots for the tolerance check"
+        L, d, mk = K.get_factor()
+        assert np.array_equal(mk, F.mark)
+        assert _rel(d, F.diag) < tol and _rel(L, F.L) < tol
+        oy, ox, _ = F.solve(E, D, ry, rx)
+        gy, gx, _ = K.solve(E, D, ry, rx)
+        assert _rel(gy, oy) < tol and _rel(gx, ox) < tol
+        A = sp.csc_matrix((lp.A, lp.iA, lp.kA), shape=(lp.m, lp.n))
+        r1 = -E * gy + A @ gx - ry            # [-E A; A^T D][y;x] = [ry;rx]  (SURVEY 3.5)
+        r2 = A.T @ gy + D * gx - rx
+        scale = max(np.abs(ry).max(), np.abs(rx).max()) + 1
+        assert max(np.abs(r1).max(), np.abs(r2).max()) <= 1e-8 * scale
+        z = np.random.default_rng(it).standard_normal(lp.m + lp.n)
+        assert _rel(K.rawsolve(z), F.rawsolve(z)) < 1e-5
+        return dict(rel_y=_rel(gy, oy), rel_x=_rel(gx, ox))
+    finally:
+        F.close()
+        K.close()
+
+
+def check_full_solve_fast(vbkkt, lib, lp, method="hsd"):
+    """FAST mode end to end on a problem of the robust list: the north_star tolerances
+    (status, iteration count +-1, objective 1e-8 relative, infeasibilities 1e-7)."""
+    st, log, x, y, _ = H.solve_via(vbkkt, lib, lp, method, mode=vbkkt.MODE_FAST)
+    north_star_tolerances(lp, method, x, y, st, log)
+    return st
+
+
 def check_full_solve(vbkkt, lib, lp, method, want_bits=True):
     """The device-resident METHOD plugin against the golden fixture: same status, byte-identical
     iteration log (the reference's golden log for hsd), bit-equal x and y."""

@@ -48,6 +48,20 @@ def test_emu_first_generation_kernels_still_bit_exact(vbkkt, emu_lib, oracle_lib
     P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("afiro"), "hsd", 26)
 
 
+@pytest.mark.parametrize("name,it,env", [("afiro", 5, {}), ("sc50b", 12, {"VBK_PANEL": "3"}),
+                                         ("sc105", 15, {"VBK_WINDOW_RHO": "0.1", "VBK_PANEL": "5"})])
+def test_emu_fast_mode_kkt_step(vbkkt, emu_lib, oracle_lib, monkeypatch, name, it, env):
+    """Fast mode: sparse part + Schur assembly + blocked dense LDL^T + dense-window sweeps, several
+    panels and a padded (rho < 1) window forced on tiny LPs."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    P.check_kkt_step_fast(vbkkt, emu_lib, oracle_lib, H.load_fixture(name), "hsd", it)
+
+
+def test_emu_fast_mode_full_solve(vbkkt, emu_lib):
+    assert P.check_full_solve_fast(vbkkt, emu_lib, H.load_fixture("afiro")) == 0
+
+
 def test_emu_kkt_step_second_problem(vbkkt, emu_lib, oracle_lib):
     P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("sc50b"), "hsd", 10)
 

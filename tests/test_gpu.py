@@ -79,6 +79,44 @@ def test_north_star_tolerances_hold(vbkkt, gpu_lib):
         P.north_star_tolerances(lp, "hsd", x, y, st, log)
 
 
+@pytest.mark.parametrize("name,it", [("afiro", 5), ("25fv47", 20), ("israel", 12), ("pilot87", 20), ("fit2p", 10)])
+def test_fast_mode_kkt_step(vbkkt, gpu_lib, oracle_lib, name, it):
+    """Fast mode (dense-window factorisation, re-associated sums) agrees with the oracle to rounding
+    on iterates without dependent pivots."""
+    P.check_kkt_step_fast(vbkkt, gpu_lib, oracle_lib, H.load_fixture(name), "hsd", it)
+
+
+@pytest.mark.parametrize("name", ["afiro", "adlittle", "blend", "israel", "sc205", "fit1d", "ship04l", "scsd1", "25fv47"])
+def test_fast_mode_full_solve_north_star_tolerances(vbkkt, gpu_lib, name):
+    """Robust-list problems solved in fast mode: status, iterations +-1, objective 1e-8."""
+    P.check_full_solve_fast(vbkkt, gpu_lib, H.load_fixture(name))
+
+
+def test_strict_mode_big_iterates_bit_equal(vbkkt, gpu_lib):
+    """The largest netlib LPs (dfl001: Lnz 7.2 M, window 2766; pds-06) at full size: the strict KKT
+    step returns the reference's solution bit for bit (fixture from the pinned oracle)."""
+    for name in ("dfl001", "pds-06"):
+        lp = H.load_fixture(name)
+        z = np.load(H.GOLDEN / "iterates" / f"{name}_it20.npz")
+        K = H.kkt_for(vbkkt, gpu_lib, lp)
+        K.factor(z["E"], z["D"])
+        sy, sx, _ = K.solve(z["E"], z["D"], z["rhs_y"], z["rhs_x"])
+        assert np.array_equal(sy, z["sol_y"]) and np.array_equal(sx, z["sol_x"])
+        K.close()
+
+
+def test_fast_mode_big_iterates_match_reference_solution(vbkkt, gpu_lib):
+    """dfl001 / pds-06 at hsd iterate 20 (committed fixtures from the pinned oracle)."""
+    for name in ("dfl001", "pds-06"):
+        lp = H.load_fixture(name)
+        z = np.load(H.GOLDEN / "iterates" / f"{name}_it20.npz")
+        K = H.kkt_for(vbkkt, gpu_lib, lp, mode=vbkkt.MODE_FAST)
+        K.factor(z["E"], z["D"])
+        sy, sx, _ = K.solve(z["E"], z["D"], z["rhs_y"], z["rhs_x"])
+        assert P._rel(sy, z["sol_y"]) < 1e-6 and P._rel(sx, z["sol_x"]) < 1e-6
+        K.close()
+
+
 def test_factor_residual_property(vbkkt, gpu_lib):
     """Size-independent property at a size the oracle is not needed for: K z = rhs after
     forwardbackward, measured with scipy (|r| small relative to |rhs|)."""
