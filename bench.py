@@ -160,7 +160,10 @@ def main():
     # dfl001 is the largest netlib LP BASELINE.json's config 2 names (FP64-bound factor, ~90 flop/B)
     ap.add_argument("--workload", default=os.environ.get("VBK_BENCH_WORKLOAD", "dfl001"))
     ap.add_argument("--iterate", type=int, default=20)
-    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    # fast = the performance mode (dense-window factorisation, re-associated sums; parity by tolerance);
+    # strict = bit-exact replay of the reference's rounding order (reported beside it at N=1)
+    ap.add_argument("--mode", default="fast", choices=["strict", "fast"])
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode side measurement")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -251,7 +254,10 @@ def main():
     if a.mode == "strict":
         assert bit_equal, f"strict mode lost bit-parity with the reference (max rel err {err:.3e})"
     else:
-        assert err < 1e-6, f"fast mode solution off by {err:.3e}"
+        sol_x = fx.cpu().numpy()
+        err_x = float(np.max(np.abs(sol_x - it["sol_x"])) / max(np.max(np.abs(it["sol_x"])), 1e-300))
+        err = max(err, err_x)
+        assert err < 1e-7, f"fast mode: KKT-step solution differs from the reference's by {err:.3e} (relative)"
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -330,7 +336,8 @@ def main():
     fac_s = float(np.mean(fac_ms)) * 1e-3
     b_fac = 12.0 * K.lnz + 8.0 * K.lnz + 2 * 12.0 * nz + 24.0 * N
     fp64_peak = float(lib.vbk_measure_fp64_tflops(local_rank))
-    roofline = {"kernel": "k_factor_tiled (strict)" if a.mode == "strict" else "factor (fast)", "bound": "hbm",
+    roofline = {"kernel": "k_factor_tiled (strict)" if a.mode == "strict" else
+                "numeric factorisation (k_factor_tiled sparse part + Schur, k_dense_diag/trsm/update_rt window)", "bound": "hbm",
                 "achieved": b_fac / fac_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": b_fac / fac_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": fac_s * 1e3, "share_of_step": fac_s * 1e3 / ms_per_step,
@@ -339,6 +346,31 @@ def main():
                          "peak_source": "measured here (DFMA yardstick kernel, vbk_measure_fp64_tflops)"},
                 "note": "strict mode replays the reference's rounding order and is latency-bound by design (SURVEY 8d)"
                 if a.mode == "strict" else ""}
+    strict = None
+    if a.mode == "fast" and not a.no_strict and world == 1:
+        # the same step in strict mode (bit-exact replay of the reference's operation order)
+        K2 = H.kkt_for(vb, lib, lp, device=local_rank, mode=vb.MODE_STRICT)
+        s2 = torch.cuda.ExternalStream(K2.stream, device=dev)
+        def step_strict():
+            with torch.cuda.stream(s2):
+                fy.copy_(ry_d); fx.copy_(rx_d); gy.copy_(b_d); gx.copy_(c_d)
+            K2.factor_dev(E_d.data_ptr(), D_d.data_ptr())
+            K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr())
+            K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), gy.data_ptr(), gx.data_ptr())
+        torch.cuda.synchronize()
+        step_strict(); K2.sync()
+        bit = bool(np.array_equal(fy.cpu().numpy(), it["sol_y"]) and np.array_equal(fx.cpu().numpy(), it["sol_x"]))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nstrict = 2
+        e0.record(s2)
+        for _ in range(nstrict):
+            step_strict()
+        e1.record(s2); K2.sync(); torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / nstrict
+        strict = {"ms_per_step": ms2, "value": flops_step / (ms2 * 1e-3) / 1e9, "unit": "GFLOP/s",
+                  "bit_equal_to_reference": bit, "factor_kernel_ms": float(lib.vbk_kkt_last_factor_kernel_ms(K2.h)),
+                  "note": "same step, strict arithmetic mode: reproduces the reference's golden logs byte for byte"}
+        K2.close()
     cpu = None
     if not a.no_cpu_baseline and world == 1:
         cpu = cpu_measure(lp, it, flops_step, a.cpu_budget, 200)
@@ -346,7 +378,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "netlib LP fixture + oracle-generated hsd iterate (tests/golden)",
            "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-           "cpu_baseline": cpu, "flops_per_step": flops_step, "rawsolves_per_step": raw_per_step,
+           "cpu_baseline": cpu, "strict_mode": strict, "flops_per_step": flops_step, "rawsolves_per_step": raw_per_step,
            "parity": {"bit_equal_to_reference": bit_equal, "max_rel_err": err},
            "symbolic": {"N": N, "lnz": K.lnz, "narth": K.narth, "levels": K.nlevels, "supernodes": K.nsupernodes}}
     print(json.dumps(out))

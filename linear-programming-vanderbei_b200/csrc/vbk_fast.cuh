@@ -37,6 +37,9 @@ struct DenseArgs {
     const int* perm; int T, n_ld;
     int* counters;
     double tol;
+    // two-level blocking (vbk_fast2.cuh): the rank-k update takes its k columns S[:, kcol0..kcol0+klen)
+    // and P[:, pcol0..pcol0+klen) and touches target rows/columns [rbase, W) x [rbase, cmax)
+    int kcol0, klen, pcol0, rbase, cmax;
 };
 
 __device__ __forceinline__ double& SW(const DenseArgs& a, int r, int c) { return a.S[(size_t)r + (size_t)c * a.ld]; }
@@ -265,6 +268,42 @@ static __global__ void k_window_store(int W, int T, int ld, const double* __rest
         for (int k = kb + blockIdx.x * blockDim.x + threadIdx.x; k < ke; k += gridDim.x * blockDim.x)
             L[k] = S[(size_t)(iL[k] - T) + (size_t)c * ld];
         if (blockIdx.x == 0 && threadIdx.x == 0) { diag[T + c] = dvec[c]; if (!wmark[c]) mark[T + c] = 0; }
+    }
+}
+
+// Schur assembly, light version: one CTA per window column, contributors applied one after the
+// other (used when the window rows see few sparse columns -- the usual case once the window is
+// padded, because nearly all flops then live inside the window; the task kernel's phase 2 handles the
+// heavy case).  S must be zero on entry.
+struct SchurArgs {
+    int N, T, ld;
+    const int* kL; const int* iL; const double* L; const double* diag;
+    const int* rowptr; const int* rk; const int* rj;       // ASCENDING row lists: sparse columns come first
+    double* S; double* wmag;
+};
+static __global__ void __launch_bounds__(kDenseThreads) k_schur_window(SchurArgs a)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = a.T + blockIdx.x; i < a.N; i += gridDim.x) {
+        double* col = a.S + (size_t)(i - a.T) * a.ld;
+        for (int k = a.kL[i] + tid; k < a.kL[i + 1]; k += nt) col[a.iL[k] - a.T] = a.L[k];   // K[:, i]
+        double d = a.diag[i], mag = fabs(d);
+        __syncthreads();
+        for (int t = a.rowptr[i]; t < a.rowptr[i + 1]; ++t) {
+            const int j = a.rj[t];
+            if (j >= a.T) break;
+            const int k = a.rk[t];
+            const double lij = a.L[k], w = lij * a.diag[j];
+            const double p = lij * w;
+            d -= p;
+            if (fabs(p) > mag) mag = fabs(p);
+            for (int kk = k + 1 + tid; kk < a.kL[j + 1]; kk += nt) {
+                double* dst = &col[a.iL[kk] - a.T];
+                *dst = fma(-w, a.L[kk], *dst);
+            }
+            __syncthreads();      // two contributors may touch the same row from different threads
+        }
+        if (tid == 0) { col[i - a.T] = d; a.wmag[i - a.T] = mag; }
     }
 }
 

@@ -1,0 +1,186 @@
+// vbk_fast2.cuh -- second-generation kernels of the dense-window factorisation (fast mode).
+//
+// Measured on B200 with the first-generation kernels of vbk_fast.cuh (dfl001, padded window W=4277,
+// 134 panels of 32): k_dense_diag 28 us, k_dense_trsm 45 us and the rank-32 update 65 us per panel --
+// launch- and latency-bound, 1.4 TFLOP/s overall.  Here:
+//   * the 32x32 diagonal block is factorised by ONE warp with the block held in registers (one row
+//     per lane, columns exchanged by shuffles): no barriers;
+//   * the row-parallel TRSM is fully unrolled (the recurrence lives in registers, not local memory);
+//   * two-level blocking: inside an outer panel of 128 columns only the panel's own strip is updated
+//     after every 32 columns; the trailing matrix gets ONE rank-128 update per outer panel, so the
+//     trailing matrix is read and written four times less often and the FP64 pipe sees 4x the work
+//     per byte (the register-tiled update kernel loops over the 128 columns in chunks of 32).
+#pragma once
+#include "vbk_fast.cuh"
+
+namespace vbk {
+
+constexpr int kOuterPanel = 4 * kPanelMax;     // 128 columns per trailing update
+
+// one warp: LDL^T of the nb x nb diagonal block at (p,p); lane r owns row r
+static __global__ void __launch_bounds__(32) k_dense_diag_w(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* blk = reinterpret_cast<double*>(raw);            // finished L11 columns, for the rare path
+    double* sd = blk + kPanelMax * (kPanelMax + 1);
+    int* skeep = reinterpret_cast<int*>(sd + kPanelMax);
+    const int lane = threadIdx.x, nb = a.nb, p = a.p;
+    const int LDB = kPanelMax + 1;
+    double row[kPanelMax];
+#pragma unroll
+    for (int c = 0; c < kPanelMax; ++c) row[c] = (lane < nb && c <= lane && c < nb) ? SW(a, p + lane, p + c) : 0.0;
+    double mymag = (lane < nb) ? a.wmag[p + lane] : 0.0;
+    double myd = 0.0;
+    int mykeep = 1;
+#pragma unroll
+    for (int c = 0; c < kPanelMax; ++c) {
+        if (c < nb) {                                           // uniform branch
+            double d = __shfl_sync(0xffffffffu, row[c], c);
+            const double magc = __shfl_sync(0xffffffffu, mymag, c);
+            int keep = 1;
+            if (fabs(d) <= a.tol * magc) {
+                // rare path (ldlt.c:600-614): max |updated column below the pivot|; rows of the block are
+                // in registers, rows below get the panel's earlier columns applied on the fly
+                double mymax = (lane > c && lane < nb) ? fabs(row[c]) : 0.0;
+                for (int r = nb + lane; r < a.W - p; r += 32) {
+                    double l[kPanelMax];
+                    for (int c1 = 0; c1 < c; ++c1) {
+                        double s = SW(a, p + r, p + c1);
+                        for (int c0 = 0; c0 < c1; ++c0) s = fma(-l[c0] * sd[c0], blk[c1 * LDB + c0], s);
+                        l[c1] = skeep[c1] ? s / sd[c1] : 0.0;
+                    }
+                    double v = SW(a, p + r, p + c);
+                    for (int c0 = 0; c0 < c; ++c0) v = fma(-l[c0] * sd[c0], blk[c * LDB + c0], v);
+                    if (fabs(v) > mymax) mymax = fabs(v);
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) { double o = __shfl_xor_sync(0xffffffffu, mymax, s); if (o > mymax) mymax = o; }
+                if (mymax < 1.0e+6 * 1.0e-8) keep = 0;
+                else d = (a.perm[a.T + p + c] < a.n_ld ? -1 : 1) * 1.0e-8;
+                if (lane == 0) atomicAdd(&a.counters[C_NDEP], 1);
+            }
+            if (lane == c) { myd = d; mykeep = keep; row[c] = d; sd[c] = d; skeep[c] = keep; }
+            double l = 0.0;
+            if (lane > c && lane < nb) { l = keep ? row[c] / d : 0.0; row[c] = l; }
+            blk[lane * LDB + c] = l;                            // column c of L11 (0 on and above the diagonal)
+            __syncwarp();
+            if (keep) {
+#pragma unroll
+                for (int c2 = c + 1; c2 < kPanelMax; ++c2) {
+                    const double lc2 = __shfl_sync(0xffffffffu, l, c2);
+                    if (c2 < nb && lane >= c2) {
+                        const double upd = l * d * lc2;
+                        row[c2] -= upd;
+                        if (lane == c2 && fabs(upd) > mymag) mymag = fabs(upd);
+                    }
+                }
+            }
+        }
+    }
+    if (lane < nb) {
+#pragma unroll
+        for (int c = 0; c < kPanelMax; ++c) if (c < lane) SW(a, p + lane, p + c) = row[c];
+        a.dvec[p + lane] = myd;
+        a.wmark[p + lane] = mykeep;
+        a.wmag[p + lane] = mymag;
+        a.pan_d[lane] = myd;
+        a.pan_keep[lane] = mykeep;
+    }
+}
+
+// rows below the block: L21 = S21 * L11^{-T} * D11^{-1}; P[:, pcol0..] = L21 * D11; trailing diagonal
+static __global__ void __launch_bounds__(kDenseThreads) k_dense_trsm_u(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* l11 = reinterpret_cast<double*>(raw);            // [kPanelMax][kPanelMax+1]
+    double* sd = l11 + kPanelMax * (kPanelMax + 1);
+    int* skeep = reinterpret_cast<int*>(sd + kPanelMax);
+    const int tid = threadIdx.x, nt = blockDim.x, nb = a.nb, p = a.p;
+    const int LDB = kPanelMax + 1;
+    for (int e = tid; e < kPanelMax * kPanelMax; e += nt) {
+        int r = e % kPanelMax, c = e / kPanelMax;
+        l11[r * LDB + c] = (r > c && r < nb) ? SW(a, p + r, p + c) : 0.0;
+    }
+    if (tid < kPanelMax) { sd[tid] = (tid < nb) ? a.pan_d[tid] : 1.0; skeep[tid] = (tid < nb) ? a.pan_keep[tid] : 0; }
+    __syncthreads();
+    for (int r = p + nb + blockIdx.x * nt + tid; r < a.W; r += gridDim.x * nt) {
+        double l[kPanelMax];
+#pragma unroll
+        for (int c = 0; c < kPanelMax; ++c) l[c] = (c < nb) ? SW(a, r, p + c) : 0.0;
+#pragma unroll
+        for (int c = 0; c < kPanelMax; ++c) {
+            double s = l[c];
+#pragma unroll
+            for (int c0 = 0; c0 < c; ++c0) s = fma(-l[c0] * sd[c0], l11[c * LDB + c0], s);
+            l[c] = skeep[c] ? s / sd[c] : 0.0;
+        }
+        double dsum = 0.0, dabs = 0.0;
+#pragma unroll
+        for (int c = 0; c < kPanelMax; ++c) {
+            if (c < nb) {
+                const double w = l[c] * sd[c];
+                SW(a, r, p + c) = l[c];
+                a.P[(size_t)r + (size_t)(a.pcol0 + c) * a.W] = w;
+                const double t = l[c] * w;
+                dsum += t;
+                if (fabs(t) > dabs) dabs = fabs(t);
+            }
+        }
+        SW(a, r, r) -= dsum;
+        if (dabs > a.wmag[r]) a.wmag[r] = dabs;
+    }
+}
+
+// rank-klen update of the strictly-lower part of S[rbase.., rbase..cmax) in kUpdTD x kUpdTD tiles
+static __global__ void __launch_bounds__(kUpdThreads) k_dense_update_k(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* As = reinterpret_cast<double*>(raw);             // [kPanelMax][kUpdTD]
+    double* Bs = As + kPanelMax * kUpdTD;
+    const int tr = blockIdx.y, tc = blockIdx.x;
+    const int r0 = a.rbase + tr * kUpdTD, c0 = a.rbase + tc * kUpdTD;
+    if (r0 + kUpdTD <= c0 || c0 >= a.cmax) return;            // tile entirely above the diagonal / outside
+    const int tid = threadIdx.x, tx = tid % kUpdTG, ty = tid / kUpdTG;
+    double acc[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[u][v] = 0.0;
+    for (int kc = 0; kc < a.klen; kc += kPanelMax) {
+        const int kn = (a.klen - kc < kPanelMax) ? (a.klen - kc) : kPanelMax;
+        __syncthreads();
+        for (int e = tid; e < kPanelMax * kUpdTD; e += kUpdThreads) {
+            const int x = e % kUpdTD, c = e / kUpdTD;
+            As[c * kUpdTD + x] = (c < kn && r0 + x < a.W) ? SW(a, r0 + x, a.kcol0 + kc + c) : 0.0;
+            Bs[c * kUpdTD + x] = (c < kn && c0 + x < a.W) ? a.P[(size_t)(c0 + x) + (size_t)(a.pcol0 + kc + c) * a.W] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int c = 0; c < kPanelMax; ++c) {
+            double av[8], bv[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                av[2 * u] = As[c * kUpdTD + 2 * tx + 2 * kUpdTG * u];
+                av[2 * u + 1] = As[c * kUpdTD + 2 * tx + 2 * kUpdTG * u + 1];
+                bv[2 * u] = Bs[c * kUpdTD + 2 * ty + 2 * kUpdTG * u];
+                bv[2 * u + 1] = Bs[c * kUpdTD + 2 * ty + 2 * kUpdTG * u + 1];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const int c2 = c0 + 2 * ty + 2 * kUpdTG * (v >> 1) + (v & 1);
+        if (c2 >= a.W || c2 >= a.cmax) continue;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = r0 + 2 * tx + 2 * kUpdTG * (u >> 1) + (u & 1);
+            if (r < a.W && r > c2) SW(a, r, c2) -= acc[u][v];
+        }
+    }
+}
+
+}  // namespace vbk

@@ -140,7 +140,7 @@ private:
     void fill_tiled_args(TiledArgs& ta);
 
     // fast mode (vbk_fast.cuh, vbk_kkt_fast.cu): dense scratch for the trailing window
-    bool fast_ready_ = false;
+    bool fast_ready_ = false, light_schur_ = false;
     int panel_nb_ = 32;
     DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_;
     DevArray<int> wmark_, pan_keep_;

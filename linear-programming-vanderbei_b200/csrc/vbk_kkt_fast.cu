@@ -1,6 +1,6 @@
 // vbk_kkt_fast.cu -- host orchestration of FAST mode (kernels in vbk_fast.cuh).
 #include "vbk_kkt.h"
-#include "vbk_fast.cuh"
+#include "vbk_fast2.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -17,13 +17,26 @@ void Kkt::prepare_fast()
     if (const char* e = std::getenv("VBK_PANEL")) panel_nb_ = std::max(1, std::min(kPanelMax, std::atoi(e)));
     else panel_nb_ = kPanelMax;
     Sw_.alloc((size_t)W * W);
-    P_.alloc((size_t)W * kPanelMax);
+    P_.alloc((size_t)W * kOuterPanel);
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
     pan_d_.alloc(kPanelMax); pan_keep_.alloc(kPanelMax);
+    {
+        // how many sparse-column contributions do the window rows see?  Few => light Schur kernel.
+        long long nsc = 0;
+        for (int i = T; i < N; ++i) {
+            const int* b = sym_.rj_asc.data() + sym_.rowptr[i];
+            const int* e = sym_.rj_asc.data() + sym_.rowptr[i + 1];
+            nsc += std::lower_bound(b, e, T) - b;
+        }
+        const char* es = std::getenv("VBK_SCHUR");
+        light_schur_ = es ? (std::string(es) == "light") : (nsc <= 128LL * W);
+    }
 #ifndef VBK_EMU
     // kernels are `static` in the headers: this translation unit launches its own copy
     VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_rt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
 #endif
     fast_ready_ = true;
@@ -44,10 +57,17 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     // 2. Schur complement of the sparse columns on the window, written densely; no dependencies.
     //    Entries outside the fill pattern are never written: start from zero.
     VBK_CUDA(cudaMemsetAsync(Sw_.p, 0, sizeof(double) * (size_t)W * W, stream_));
-    VBK_LAUNCH(k_zero_counter, 1, 32, 0, stream_, counters_.p, (int)C_NEXT);
-    ta.phase = 2; ta.task_base = sparse_tasks; ta.ntasks = sym_.ntasks() - sparse_tasks;
-    ta.T = T; ta.ldw = W; ta.Sw = Sw_.p; ta.wmag = wmag_.p;
-    VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(ta.ntasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
+    if (light_schur_) {
+        SchurArgs sc;
+        sc.N = N; sc.T = T; sc.ld = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
+        sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;
+        VBK_LAUNCH(k_schur_window, std::min(W, num_sms_ * 8), kDenseThreads, 0, stream_, sc);
+    } else {
+        VBK_LAUNCH(k_zero_counter, 1, 32, 0, stream_, counters_.p, (int)C_NEXT);
+        ta.phase = 2; ta.task_base = sparse_tasks; ta.ntasks = sym_.ntasks() - sparse_tasks;
+        ta.T = T; ta.ldw = W; ta.Sw = Sw_.p; ta.wmag = wmag_.p;
+        VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(ta.ntasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
+    }
 
     // 3. blocked right-looking dense LDL^T of the window
     DenseArgs da;
@@ -65,7 +85,41 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     const char* eu = std::getenv("VBK_UPDATE");
     const bool simple_update = eu && std::string(eu) == "simple";
     int launches = 2;
-    for (int p = 0; p < W; p += panel_nb_) {
+    const char* ed = std::getenv("VBK_DENSE");
+    const bool dense_v1 = ed && std::string(ed) == "v1";
+    if (!dense_v1) {
+        // two-level blocking (vbk_fast2.cuh): inner panels of panel_nb_ columns, one rank-(outer) update of
+        // the trailing matrix per outer panel
+        const size_t sm_diag_w = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;
+        const int outer = std::max(panel_nb_, (kOuterPanel / kPanelMax) * panel_nb_);
+        for (int P0 = 0; P0 < W; P0 += outer) {
+            const int kend = std::min(P0 + outer, W);
+            for (int p = P0; p < kend; p += panel_nb_) {
+                da.p = p; da.nb = std::min(panel_nb_, kend - p);
+                da.pcol0 = p - P0;
+                VBK_LAUNCH(k_dense_diag_w, 1, 32, sm_diag_w, stream_, da);
+                ++launches;
+                const int below = W - p - da.nb;
+                if (below <= 0) continue;
+                const int g = std::min((below + kDenseThreads - 1) / kDenseThreads, num_sms_ * 4);
+                VBK_LAUNCH(k_dense_trsm_u, g, kDenseThreads, sm_trsm, stream_, da);
+                ++launches;
+                if (kend - (p + da.nb) > 0) {        // the rest of the outer panel's own strip
+                    da.kcol0 = p; da.klen = da.nb; da.rbase = p + da.nb; da.cmax = kend;
+                    const int tr = (W - da.rbase + kUpdTD - 1) / kUpdTD, tc = (kend - da.rbase + kUpdTD - 1) / kUpdTD;
+                    VBK_LAUNCH(k_dense_update_k, dim3(tc, tr), kUpdThreads, sm_upd_rt, stream_, da);
+                    ++launches;
+                }
+            }
+            if (W - kend > 0) {                        // trailing matrix: one rank-(kend-P0) update
+                da.kcol0 = P0; da.klen = kend - P0; da.pcol0 = 0; da.rbase = kend; da.cmax = W;
+                const int tiles = (W - kend + kUpdTD - 1) / kUpdTD;
+                VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
+                ++launches;
+            }
+        }
+    }
+    for (int p = 0; dense_v1 && p < W; p += panel_nb_) {
         da.p = p; da.nb = std::min(panel_nb_, W - p);
         VBK_LAUNCH(k_dense_diag, 1, kDenseThreads, sm_diag, stream_, da);
         ++launches;
