@@ -17,6 +17,31 @@ namespace vbk {
 
 constexpr int kOuterPanel = 4 * kPanelMax;     // 128 columns per trailing update
 
+// rare path of the pivot rule (ldlt.c:600-614), kept out of line so that the unrolled main path of
+// k_dense_diag_w stays small enough for the instruction cache: max |updated column c below the pivot|
+// over the rows below the block (the block's own rows are handled by the caller from registers)
+#ifndef VBK_EMU
+__noinline__
+#endif
+__device__ double dense_colmax_below(const DenseArgs& a, int c, int lane, const double* blk,
+                                                  const double* sd, const int* skeep)
+{
+    const int LDB = kPanelMax + 1, p = a.p, nb = a.nb;
+    double mymax = 0.0;
+    for (int r = nb + lane; r < a.W - p; r += 32) {
+        double l[kPanelMax];
+        for (int c1 = 0; c1 < c; ++c1) {
+            double s = SW(a, p + r, p + c1);
+            for (int c0 = 0; c0 < c1; ++c0) s = fma(-l[c0] * sd[c0], blk[c1 * LDB + c0], s);
+            l[c1] = skeep[c1] ? s / sd[c1] : 0.0;
+        }
+        double v = SW(a, p + r, p + c);
+        for (int c0 = 0; c0 < c; ++c0) v = fma(-l[c0] * sd[c0], blk[c * LDB + c0], v);
+        if (fabs(v) > mymax) mymax = fabs(v);
+    }
+    return mymax;
+}
+
 // one warp: LDL^T of the nb x nb diagonal block at (p,p); lane r owns row r
 static __global__ void __launch_bounds__(32) k_dense_diag_w(DenseArgs a)
 {
@@ -42,17 +67,8 @@ static __global__ void __launch_bounds__(32) k_dense_diag_w(DenseArgs a)
                 // rare path (ldlt.c:600-614): max |updated column below the pivot|; rows of the block are
                 // in registers, rows below get the panel's earlier columns applied on the fly
                 double mymax = (lane > c && lane < nb) ? fabs(row[c]) : 0.0;
-                for (int r = nb + lane; r < a.W - p; r += 32) {
-                    double l[kPanelMax];
-                    for (int c1 = 0; c1 < c; ++c1) {
-                        double s = SW(a, p + r, p + c1);
-                        for (int c0 = 0; c0 < c1; ++c0) s = fma(-l[c0] * sd[c0], blk[c1 * LDB + c0], s);
-                        l[c1] = skeep[c1] ? s / sd[c1] : 0.0;
-                    }
-                    double v = SW(a, p + r, p + c);
-                    for (int c0 = 0; c0 < c; ++c0) v = fma(-l[c0] * sd[c0], blk[c * LDB + c0], v);
-                    if (fabs(v) > mymax) mymax = fabs(v);
-                }
+                const double below = dense_colmax_below(a, c, lane, blk, sd, skeep);
+                if (below > mymax) mymax = below;
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) { double o = __shfl_xor_sync(0xffffffffu, mymax, s); if (o > mymax) mymax = o; }
                 if (mymax < 1.0e+6 * 1.0e-8) keep = 0;
@@ -180,6 +196,114 @@ static __global__ void __launch_bounds__(kUpdThreads) k_dense_update_k(DenseArgs
             const int r = r0 + 2 * tx + 2 * kUpdTG * (u >> 1) + (u & 1);
             if (r < a.W && r > c2) SW(a, r, c2) -= acc[u][v];
         }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Dense-window triangular sweeps on many CTAs.  After the factorisation the strictly-lower L of the
+// window is mirrored into the upper triangle of the scratch matrix (k_window_mirror), so that the
+// backward sweep (L^T) reads rows of the same column-major array as the forward sweep (L): both become
+//     z[R_p] = T_pp^{-1} ( z[R_p] - sum_q  S[R_p, C_q] z[C_q] )      q < p forward, q > p backward
+// over 32-row panels.  Panels are dealt round-robin to the CTAs; a panel's CTA multiplies the
+// 32x32 blocks of its panel row as soon as the corresponding z[C_q] is published (one flag per
+// panel), its warps sharing the blocks; the block of the panel that finishes last is already in
+// registers when its flag flips, so the critical path per panel is one 32x32 mat-vec, a shared-memory
+// reduction, the 32-step diagonal solve and one flag hand-off.
+// --------------------------------------------------------------------------------------------
+static __global__ void k_window_mirror(int W, int ld, double* __restrict__ S)
+{
+    VBK_DYN_SMEM(raw);
+    double* t = reinterpret_cast<double*>(raw);      // [32][33]
+    const int bx = blockIdx.x, by = blockIdx.y;      // tile (rows by, cols bx) of the lower triangle
+    if (by < bx) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
+    for (int c = ty; c < 32; c += nty) {
+        const int r = by * 32 + tx, cc = bx * 32 + c;
+        t[c * 33 + tx] = (r < W && cc < W && r > cc) ? S[(size_t)r + (size_t)cc * ld] : 0.0;
+    }
+    __syncthreads();
+    for (int c = ty; c < 32; c += nty) {
+        // element (row = bx*32+tx, col = by*32+c) of the upper triangle = L[by*32+c, bx*32+tx]
+        const int r = bx * 32 + tx, cc = by * 32 + c;
+        if (r < W && cc < W && r < cc) S[(size_t)r + (size_t)cc * ld] = t[tx * 33 + c];
+    }
+}
+
+#ifdef VBK_EMU
+constexpr int kTriThreads = 64;
+#else
+constexpr int kTriThreads = 256;
+#endif
+
+struct TriArgs {
+    int W, ld, npanels, dir;       // dir 0: forward (lower), 1: backward (upper)
+    const double* S; double* z; const int* mark;     // z, mark already offset to the window
+    int* flags; int* counters; const unsigned long long* scal_bits; double epssol;
+};
+
+static __global__ void __launch_bounds__(kTriThreads) k_window_tri(TriArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* part = reinterpret_cast<double*>(raw);            // [nwarps][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const double eps = a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;
+    for (int pp = blockIdx.x; pp < a.npanels; pp += gridDim.x) {
+        const int p = a.dir ? a.npanels - 1 - pp : pp;
+        const int row = 32 * p + lane;
+        const bool rok = row < a.W;
+        double acc = 0.0;
+        const int nblk = a.dir ? (a.npanels - 1 - p) : p;
+        for (int bi = warp; bi < nblk; bi += nwarps) {
+            const int q = a.dir ? (a.npanels - 1 - bi) : bi;
+            double blk[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int col = 32 * q + c;
+                blk[c] = (rok && col < a.W) ? a.S[(size_t)row + (size_t)col * a.ld] : 0.0;
+            }
+            if (lane == 0) {
+                while (vbk_ld_volatile(&a.flags[q]) == 0) __nanosleep(20);
+                __threadfence();
+            }
+            __syncwarp();
+            const double zq = (32 * q + lane < a.W) ? __ldcg(&a.z[32 * q + lane]) : 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc = fma(blk[c], __shfl_sync(0xffffffffu, zq, c), acc);
+        }
+        part[warp * 32 + lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double v = rok ? a.z[row] : 0.0;
+            for (int w = 0; w < nwarps; ++w) v -= part[w * 32 + lane];
+            const int mk = rok ? a.mark[row] : 1;
+            double tri[32];                                     // this lane's row of the diagonal block
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int col = 32 * p + c;
+                const bool use = a.dir ? (c > lane) : (c < lane);
+                tri[c] = (use && rok && col < a.W) ? a.S[(size_t)row + (size_t)col * a.ld] : 0.0;
+            }
+            if (!a.dir) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (lane == c && !mk) { if (fabs(v) > eps) a.counters[C_CONSISTENT] = 0; else v = 0.0; }
+                    const double zc = __shfl_sync(0xffffffffu, v, c);
+                    if (tri[c] != 0.0) v = fma(-tri[c], zc, v);
+                }
+            } else {
+#pragma unroll
+                for (int c = 31; c >= 0; --c) {
+                    if (lane == c && !mk) { if (fabs(v) > eps) a.counters[C_CONSISTENT] = 0; else v = 0.0; }
+                    const double zc = __shfl_sync(0xffffffffu, v, c);
+                    if (tri[c] != 0.0) v = fma(-tri[c], zc, v);
+                }
+            }
+            if (rok) a.z[row] = v;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicExch(&a.flags[p], 1);
+        }
+        __syncthreads();
     }
 }
 

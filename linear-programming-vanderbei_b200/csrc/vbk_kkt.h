@@ -143,7 +143,7 @@ private:
     bool fast_ready_ = false, light_schur_ = false;
     int panel_nb_ = 32;
     DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_;
-    DevArray<int> wmark_, pan_keep_;
+    DevArray<int> wmark_, pan_keep_, tri_flags_;
     void prepare_fast();
     void factor_window_fast(TiledArgs& ta);
     void rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_smem);

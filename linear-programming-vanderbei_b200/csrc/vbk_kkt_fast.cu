@@ -20,6 +20,7 @@ void Kkt::prepare_fast()
     P_.alloc((size_t)W * kOuterPanel);
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
     pan_d_.alloc(kPanelMax); pan_keep_.alloc(kPanelMax);
+    tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
     {
         // how many sparse-column contributions do the window rows see?  Few => light Schur kernel.
         long long nsc = 0;
@@ -137,7 +138,13 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             launches += 2;
         }
     }
-    // 4. back into the packed storage the solves and the tests read
+    // 4. mirror L into the upper triangle (the backward sweep then reads rows, like the forward one)
+    {
+        const int nt32 = (W + 31) / 32;
+        VBK_LAUNCH(k_window_mirror, dim3(nt32, nt32), kVecThreads, 32 * 33 * sizeof(double), stream_, W, W, Sw_.p);
+        ++launches;
+    }
+    // 5. back into the packed storage the strict-layout consumers (tests, get_factor) read
     {
         const int gx = std::max(1, std::min((W + kVecThreads - 1) / kVecThreads, 64));
         const int gy = std::max(1, std::min(W, 1024));
@@ -163,9 +170,27 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
     if (T > 0) VBK_LAUNCH(k_fwd_flags, gsolve, kSolveThreads, flag_smem, stream_, fs);
     VBK_LAUNCH(k_window_gather, ggather, kSolveThreads, 0, stream_, wa);
-    VBK_LAUNCH(k_window_fwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    const char* ew = std::getenv("VBK_WSOLVE");
+    const bool wsolve_v1 = ew && std::string(ew) == "v1";
+    TriArgs tr;
+    const int W = N - T;
+    tr.W = W; tr.ld = W; tr.npanels = (W + 31) / 32; tr.S = Sw_.p; tr.z = z_.p + T; tr.mark = mark_.p + T;
+    tr.flags = tri_flags_.p; tr.counters = counters_.p; tr.scal_bits = bits_.p; tr.epssol = 1.0e-6;
+    const int gtri = std::max(1, std::min(tr.npanels, num_sms_));
+    const size_t sm_tri = (size_t)(kTriThreads / 32) * 32 * sizeof(double);
+    if (wsolve_v1) VBK_LAUNCH(k_window_fwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    else {
+        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)tr.npanels, stream_));
+        tr.dir = 0;
+        VBK_LAUNCH(k_window_tri, gtri, kTriThreads, sm_tri, stream_, tr);
+    }
     VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
-    VBK_LAUNCH(k_window_bwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    if (wsolve_v1) VBK_LAUNCH(k_window_bwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    else {
+        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)tr.npanels, stream_));
+        tr.dir = 1;
+        VBK_LAUNCH(k_window_tri, gtri, kTriThreads, sm_tri, stream_, tr);
+    }
     VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
     if (T > 0) VBK_LAUNCH(k_bwd_flags, gsolve, kSolveThreads, flag_smem, stream_, fs);
     VBK_CHECK_LAUNCH();
