@@ -17,6 +17,12 @@ ldltfac / forwardbackward), pinned host arrays, H2D+D2H inside the timed region.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload pilot87] [--mode strict|fast]
+
+Two more workloads cover the multi-GPU rows of SURVEY.md 8e (run them under torchrun for N > 1):
+    --workload batch      BASELINE config 4: batches of independent random sparse LPs (m=2000, n=4000),
+                          LP i on rank i mod N, no collective; metric LPs/s
+    --workload rowblock   BASELINE config 5: row-block smx / transpose-smx + dot / max-norm all-reduce on the
+                          synthetic multicommodity LP (default R=100, K=126: m=2.56e6, n=4.99e6); metric GB/s
 """
 from __future__ import annotations
 
@@ -151,6 +157,229 @@ def cpu_measure(lp, it, flops_per_step, budget_s, max_steps):
             "ms_per_step": dt * 1e3}
 
 
+def _clock_fields(sampler):
+    return sampler.summary()
+
+
+def multi_gpu_workload(a, rank, local_rank, world):
+    """BASELINE configs 4 (batch of independent LPs) and 5 (row-block smx + all-reduce).  One process per
+    GPU; barrier + synchronize on both sides of the timed region; max over ranks."""
+    import torch
+    import torch.distributed as dist
+    vb = _load("vbkkt", ROOT / "linear-programming-vanderbei_b200" / "__init__.py")
+    import harness as H
+    mode = vb.MODE_STRICT if a.mode == "strict" else vb.MODE_FAST
+
+    if a.impl == "reference":
+        # the reference's own CPU path for the same unit of work, rank 0 only
+        if rank != 0:
+            return
+        if a.workload == "batch":
+            ref = H.load_ref("hsd")
+            fn, kind = (ref.solver, "reference") if ref is not None else (None, "port")
+            if fn is None:
+                subprocess.run(["make", "-C", str(ROOT / "oracle"), "restatement"], check=True, stdout=subprocess.DEVNULL)
+                fn = H.declare_oracle(C.CDLL(str(ROOT / "oracle" / "libkkt_oracle.so"))).kko_solver_hsd
+            lp = vb.workloads.random_sparse_lp(0, a.batch_m, a.batch_n)
+            t0 = time.perf_counter()
+            st, log, x, y = H.call_solver(fn, lp)
+            dt = time.perf_counter() - t0
+            v = 1.0 / dt
+            print(json.dumps({"impl": "reference", "metric": "independent LPs solved per second (hsd)", "value": v,
+                              "unit": "LP/s", "n_gpus": a.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                              "data": "synthetic random sparse LP, seed 0",
+                              "config": {"workload": f"batch of random sparse LPs m={a.batch_m} n={a.batch_n} (8 nnz/col)"},
+                              "cpu_baseline": {"value": v, "unit": "LP/s", "cores": 1, "kind": kind,
+                                               "sample": f"1 LP, {len(H.iteration_lines(log))} iterations, status {st}, {dt:.1f} s on 1 host core"},
+                              "e2e": {"value": v, "unit": "LP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        else:
+            lp = vb.workloads.multicommodity_lp(a.grid, a.commodities)
+            kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+            ref = H.load_ref("hsd")
+            rng = np.random.default_rng(1)
+            x, y = rng.standard_normal(lp.n), rng.standard_normal(lp.m)
+            rho, sig = np.zeros(lp.m), np.zeros(lp.n)
+            if ref is not None:
+                smx, dot, mxv, kind = ref.smx, ref.dotprod, ref.maxv, "reference"
+            else:
+                subprocess.run(["make", "-C", str(ROOT / "oracle"), "restatement"], check=True, stdout=subprocess.DEVNULL)
+                o = H.declare_oracle(C.CDLL(str(ROOT / "oracle" / "libkkt_oracle.so")))
+                smx, dot, mxv, kind = o.kko_smx, o.kko_dotprod, o.kko_maxv, "port"
+            smx.argtypes = [C.c_int, C.c_int, H.c_double_p, H.c_int_p, H.c_int_p, H.c_double_p, H.c_double_p]
+            dot.argtypes, dot.restype = [H.c_double_p, H.c_double_p, C.c_int], C.c_double
+            mxv.argtypes, mxv.restype = [H.c_double_p, C.c_int], C.c_double
+            def step():
+                smx(lp.m, lp.n, H.ptr_d(lp.A), H.ptr_i(lp.kA), H.ptr_i(lp.iA), H.ptr_d(x), H.ptr_d(rho))
+                smx(lp.n, lp.m, H.ptr_d(At), H.ptr_i(kAt), H.ptr_i(iAt), H.ptr_d(y), H.ptr_d(sig))
+                dot(H.ptr_d(x), H.ptr_d(sig), lp.n); dot(H.ptr_d(y), H.ptr_d(rho), lp.m)
+                dot(H.ptr_d(rho), H.ptr_d(rho), lp.m); dot(H.ptr_d(sig), H.ptr_d(sig), lp.n)
+                mxv(H.ptr_d(rho), lp.m); mxv(H.ptr_d(sig), lp.n)
+            bytes_step = rowblock_bytes(lp.m, lp.n, lp.nz)
+            for _ in range(a.warmup):
+                step()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                step()
+            dt = (time.perf_counter() - t0) / a.steps
+            v = bytes_step / dt / 1e9
+            print(json.dumps({"impl": "reference", "metric": "row-block smx + dot/maxv GB/s", "value": v, "unit": "GB/s",
+                              "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                              "data": "synthetic multicommodity LP",
+                              "config": {"workload": f"multicommodity R={a.grid} K={a.commodities}: m={lp.m} n={lp.n} nz={lp.nz}"},
+                              "cpu_baseline": {"value": v, "unit": "GB/s", "cores": 1, "kind": kind,
+                                               "sample": f"{a.steps} steps (2 smx + 4 dotprod + 2 maxv), {dt * 1e3:.1f} ms/step, 1 host core"},
+                              "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    lib = vb.load()
+    if lib.vbk_device_count() < 1 or not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    a.warmup = max(a.warmup, 3) if a.workload == "rowblock" else max(a.warmup, 1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    if a.workload == "batch":
+        B = a.batch_per_gpu
+        nlp = B * world
+        gen = lambda i: vb.workloads.random_sparse_lp(i, a.batch_m, a.batch_n)
+        mine = [gen(i) for i in vb.batch.shard(nlp, rank, world)]
+        vb.batch.solve_local(lib, mine[:1], "hsd", local_rank, mode, 1)              # warm-up (module load, allocator)
+        for _ in range(a.warmup - 1):
+            vb.batch.solve_local(lib, mine[:min(len(mine), a.streams)], "hsd", local_rank, mode, a.streams)
+        sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        res = None
+        for _ in range(a.steps):
+            res = vb.batch.solve_local(lib, mine, "hsd", local_rank, mode, a.streams)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        clocks = sampler.summary()
+        ok = all(r["status"] == 0 for r in res)
+        its = float(np.mean([r["iterations"] for r in res]))
+        gap = float(max(abs(r["primal_obj"] - r["dual_obj"]) / max(1.0, abs(r["primal_obj"])) for r in res))
+        if rank == 0:
+            v = nlp * a.steps / dt
+            nbytes_in = sum(12 * lp.nz + 4 * (lp.n + 1) + 8 * (lp.m + lp.n) for lp in mine)
+            out = {"metric": "independent LPs solved per second (hsd)", "value": v, "unit": "LP/s", "n_gpus": world,
+                   "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic random sparse LPs (seed = LP index)",
+                   "config": {"workload": f"batch of {nlp} random sparse LPs m={a.batch_m} n={a.batch_n} (8 nnz/col), "
+                                          f"{B} per GPU, LP i on rank i mod {world}", "mode": a.mode,
+                              "streams_per_gpu": a.streams, "l2": "each LP's factor (Lnz*8 B) exceeds nothing: working sets rotate across LPs",
+                              "parallelism": f"{world} rank(s), no collective on the data path"},
+                   "e2e": {"value": v, "unit": "LP/s", "h2d_bytes_per_step": int(nbytes_in),
+                           "d2h_bytes_per_step": int(sum(8 * (lp.m + lp.n) for lp in mine)),
+                           "note": "vbk_solve_batch takes host arrays and returns host x,y: the timed region is end to end"},
+                   "gpu_launches": None, "clocks": clocks,
+                   "parity": {"all_optimal": bool(ok), "mean_iterations": its, "max_rel_duality_gap": gap}}
+            print(json.dumps(out))
+    else:
+        lp = vb.workloads.multicommodity_lp(a.grid, a.commodities)
+        kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+        ops = vb.rowblock.RowBlockOps(lib, lp.m, lp.n, lp.kA, lp.iA, lp.A, kAt, iAt, At, dev)
+        rng = np.random.default_rng(1)
+        x, y = rng.standard_normal(lp.n), rng.standard_normal(lp.m)
+        lx, ly = ops.local_x(x), ops.local_y(y)
+        rho = torch.zeros(ops.rows_per, dtype=torch.float64, device=dev)
+        sig = torch.zeros(ops.cols_per, dtype=torch.float64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def step():
+            ops.A_x(lx, rho)                       # hsd.c:182
+            ops.At_y(ly, sig)                      # hsd.c:191
+            d = ops.dots([(lx, sig), (ly, rho), (rho, rho), (sig, sig)]).clone()
+            mx = ops.absmax([rho, sig]).clone()
+            return d, mx
+        for _ in range(a.warmup):
+            d, mx = step()
+        # parity: the distributed products against a host computation of the same sums
+        import scipy.sparse as sp
+        Acsr = sp.csc_matrix((lp.A, lp.iA, lp.kA), shape=(lp.m, lp.n)).tocsr()
+        rho_ref = Acsr[ops.r0:ops.r1] @ x
+        err = float(np.max(np.abs(rho.cpu().numpy()[: ops.r1 - ops.r0] - rho_ref)) / max(1.0, np.max(np.abs(rho_ref))))
+        dref = float(y @ (Acsr @ x))
+        derr = abs(float(d[1]) - dref) / max(1.0, abs(dref))
+        assert err < 1e-12 and derr < 1e-10, (err, derr)
+        sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        barrier()
+        for s in range(a.steps):
+            flush.fill_(s & 0xFF)
+            barrier()
+            ev[s][0].record()
+            step()
+            ev[s][1].record()
+        barrier()
+        ms = max_over_ranks(float(sum(e0.elapsed_time(e1) for e0, e1 in ev)) / a.steps)
+        clocks = sampler.summary()
+        # e2e: host vectors in, host results out, per step
+        hx, hy = torch.from_numpy(x[ops.c0:ops.c1].copy()).pin_memory(), torch.from_numpy(y[ops.r0:ops.r1].copy()).pin_memory()
+        hrho, hsig = torch.empty(ops.r1 - ops.r0, dtype=torch.float64).pin_memory(), torch.empty(ops.c1 - ops.c0, dtype=torch.float64).pin_memory()
+        def step_host():
+            lx[: ops.c1 - ops.c0].copy_(hx, non_blocking=True); ly[: ops.r1 - ops.r0].copy_(hy, non_blocking=True)
+            d, mx = step()
+            hrho.copy_(rho[: ops.r1 - ops.r0], non_blocking=True); hsig.copy_(sig[: ops.c1 - ops.c0], non_blocking=True)
+            return d.cpu(), mx.cpu()
+        step_host(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            step_host()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / a.steps)
+        if rank == 0:
+            total_bytes = rowblock_bytes(lp.m, lp.n, lp.nz)
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            v = total_bytes / (ms * 1e-3) / 1e9
+            out = {"metric": "row-block smx + dot/maxv GB/s", "value": v, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
+                   "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                   "dtype": "f64", "data": "synthetic multicommodity LP (generator seed 1)",
+                   "config": {"workload": f"multicommodity R={a.grid} K={a.commodities}: m={lp.m} n={lp.n} nz={lp.nz}; step = A x + A^T y "
+                                          "(all-gather + row-block SpMV each) + 4 dot products + 2 max-norms (one all-reduce each)",
+                              "l2": "flushed between timed steps (256 MiB write)",
+                              "parallelism": f"row blocks over {world} rank(s); NCCL all-gather of x,y and all-reduce of 4+2 doubles"},
+                   "e2e": {"value": total_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
+                           "h2d_bytes_per_step": int(8 * (ops.c1 - ops.c0 + ops.r1 - ops.r0)),
+                           "d2h_bytes_per_step": int(8 * (ops.c1 - ops.c0 + ops.r1 - ops.r0) + 48)},
+                   "gpu_launches": 5 * a.steps, "clocks": clocks,
+                   "roofline": {"kernel": "k_spmv_rows + k_dot_partial/k_absmax_partial (whole step)", "bound": "hbm",
+                                "achieved": v / world, "peak": hbm, "unit": "GB/s", "frac": v / world / hbm, "traffic": None,
+                                "note": "per-GPU algorithmic bytes (12 B per nonzero, 8 B per vector entry read or written) over the step time, collectives included"},
+                   "parity": {"max_rel_err_Ax": err, "rel_err_dot": derr}}
+            print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def rowblock_bytes(m, n, nz):
+    """Algorithmic bytes of one step: two smx (12 B per nonzero + pointers + input + output vector),
+    four dot products (16 B per entry), two max-norms (8 B per entry)."""
+    smx1 = 12 * nz + 4 * (m + 1) + 8 * n + 8 * m
+    smx2 = 12 * nz + 4 * (n + 1) + 8 * m + 8 * n
+    dots = 16 * (n + m + m + n)
+    mx = 8 * (m + n)
+    return smx1 + smx2 + dots + mx
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +393,12 @@ def main():
     # strict = bit-exact replay of the reference's rounding order (reported beside it at N=1)
     ap.add_argument("--mode", default="fast", choices=["strict", "fast"])
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode side measurement")
+    ap.add_argument("--batch-per-gpu", type=int, default=8, help="batch workload: LPs per GPU per step")
+    ap.add_argument("--batch-m", type=int, default=2000)
+    ap.add_argument("--batch-n", type=int, default=4000)
+    ap.add_argument("--streams", type=int, default=4, help="batch workload: solver streams in flight per GPU")
+    ap.add_argument("--grid", type=int, default=100, help="rowblock workload: grid side R")
+    ap.add_argument("--commodities", type=int, default=126, help="rowblock workload: K")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -172,6 +407,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if a.workload in ("batch", "rowblock"):
+        return multi_gpu_workload(a, rank, local_rank, world)
 
     lp, it = load_workload(a.workload, a.iterate)
     N, nz = lp.m + lp.n, lp.nz

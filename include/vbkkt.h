@@ -111,6 +111,42 @@ int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const i
                  const double *A, const double *b, const double *c, double f,
                  double *x, double *y, vbk_profile *prof);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batches of independent LPs (BASELINE.json config 4).  No reference equivalent: the reference
+ * solves one LP per process through `solver` (src/common/solve.c:237); a batch is `nlp` such calls,
+ * `nstreams` of them in flight at once on `device`, each with its own factor object and CUDA stream.
+ * Across GPUs the caller deals the batch round-robin, one process per GPU, no collective.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vbk_lp_desc {
+    int m, n, nz;                     /* solver-space dimensions, as passed to `solver` */
+    const int *iA, *kA;               /* CSC row indices [nz], column pointers [n+1]    */
+    const double *A, *b, *c;          /* values [nz], right-hand side [m], objective [n] */
+    double f;                         /* objective offset                                 */
+    double *x, *y;                    /* out: primal [n], dual [m] (caller-allocated)     */
+    int status, iterations;           /* out: solver() return code, iteration count       */
+    double primal_obj, dual_obj;      /* out: c.x + f, b.y + f (solve.c:254-255)          */
+    double seconds;                   /* out: wall time of this LP's solve                */
+} vbk_lp_desc;
+/* method: 0 = hsd, 1 = intpt.  Returns the number of LPs whose status is not 0. */
+int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp_desc *lps, int nstreams);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-block partitioned smx / dotprod / maxv (BASELINE.json config 5): the per-rank pieces.  Device
+ * pointers, asynchronous on `stream` (a cudaStream_t); the all-gather / all-reduce between them is the
+ * caller's (NCCL through torch.distributed, see rowblock.py).
+ * ---------------------------------------------------------------------------------------------- */
+/* y[r] = sum_k val[k] * x[idx[k]], k in [ptr[r], ptr[r+1]), ascending k: with the rows of a matrix in
+ * ascending column order this is the summation order of the reference's smx (linalg.c:62-70). */
+void vbk_spmv_rows_dev(int nrows, const int *ptr_dev, const int *idx_dev, const double *val_dev,
+                       const double *x_dev, double *y_dev, void *stream);
+/* out_dev[q] = x_q . y_q over n[q] local entries, q < count <= 8 (fixed-shape tree: deterministic, not the
+ * reference's left-to-right order of linalg.c:17-25).  scratch_dev: vbk_reduce_scratch_doubles() doubles. */
+void vbk_dots_partial_dev(int count, const double *const *x_dev, const double *const *y_dev, const long long *n,
+                          double *out_dev, double *scratch_dev, void *stream);
+/* out_dev[q] = max_i |x_q[i]| (linalg.c:108-116), q < count <= 8 */
+void vbk_absmax_partial_dev(int count, const double *const *x_dev, const long long *n, double *out_dev, void *stream);
+int  vbk_reduce_scratch_doubles(void);
+
 /* MAX_ITER is a compile-time 200 in the reference (hsd.c:25, intpt.c:31); <=0 restores it */
 void vbk_set_iteration_limit(int itnlim);
 /* device time (ms, CUDA events on the handle's stream) of the last numeric-factor kernel */

@@ -13,7 +13,9 @@ library's "no CUDA device" message (only the host-side symbolic analysis works w
 from __future__ import annotations
 
 import ctypes as C
+import importlib.util
 import os
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -114,6 +116,25 @@ def _declare(lib):
 
 
 _LIBS = {}
+
+
+def _submodule(name):
+    """batch / rowblock / workloads live beside this file; the directory name has a hyphen, so they are
+    loaded by path and registered as ``<this module>.<name>``."""
+    full = f"{__name__}.{name}"
+    if full in sys.modules:
+        return sys.modules[full]
+    spec = importlib.util.spec_from_file_location(full, PKG_DIR / f"{name}.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[full] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def __getattr__(name):
+    if name in ("batch", "rowblock", "workloads"):
+        return _submodule(name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 def load(path=None):

@@ -247,7 +247,15 @@ static __global__ void __launch_bounds__(kTriThreads) k_window_tri(TriArgs a)
     double* part = reinterpret_cast<double*>(raw);            // [nwarps][32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const double eps = a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;
-    for (int pp = blockIdx.x; pp < a.npanels; pp += gridDim.x) {
+    volatile int* s_claimp = reinterpret_cast<volatile int*>(part + nwarps * 32);   // after part[nwarps][32]
+    for (;;) {
+        // panels are CLAIMED in dependency order (flags[npanels] is the claim counter): a panel some CTA
+        // waits for is always owned by a CTA that is already running, whatever else shares the GPU
+        // (the batch driver runs many of these sweeps concurrently on different streams)
+        if (tid == 0) *s_claimp = atomicAdd(&a.flags[a.npanels], 1);
+        __syncthreads();
+        const int pp = *s_claimp;
+        if (pp >= a.npanels) break;
         const int p = a.dir ? a.npanels - 1 - pp : pp;
         const int row = 32 * p + lane;
         const bool rok = row < a.W;

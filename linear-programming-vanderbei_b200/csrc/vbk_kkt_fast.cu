@@ -79,6 +79,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     // (|value| < ulp(T)/2) and is then cancelled exactly.  With re-associated sums the same pivot comes
     // out as the tiny true value instead, so the test is |d| <= 2^-52 * (largest term magnitude).
     da.tol = 2.220446049250313e-16;
+    if (const char* e = std::getenv("VBK_PIVOT_TOL_ULPS")) da.tol *= std::max(0.0, std::atof(e));
     const size_t sm_diag = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax + kDenseThreads) + sizeof(int) * kPanelMax;
     const size_t sm_trsm = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;
     const size_t sm_upd = sizeof(double) * 2 * kPanelMax * kTileDim;
@@ -177,17 +178,17 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     tr.W = W; tr.ld = W; tr.npanels = (W + 31) / 32; tr.S = Sw_.p; tr.z = z_.p + T; tr.mark = mark_.p + T;
     tr.flags = tri_flags_.p; tr.counters = counters_.p; tr.scal_bits = bits_.p; tr.epssol = 1.0e-6;
     const int gtri = std::max(1, std::min(tr.npanels, num_sms_));
-    const size_t sm_tri = (size_t)(kTriThreads / 32) * 32 * sizeof(double);
+    const size_t sm_tri = (size_t)(kTriThreads / 32) * 32 * sizeof(double) + 16;   // + the claim slot
     if (wsolve_v1) VBK_LAUNCH(k_window_fwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
     else {
-        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)tr.npanels, stream_));
+        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)(tr.npanels + 1), stream_));
         tr.dir = 0;
         VBK_LAUNCH(k_window_tri, gtri, kTriThreads, sm_tri, stream_, tr);
     }
     VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
     if (wsolve_v1) VBK_LAUNCH(k_window_bwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
     else {
-        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)tr.npanels, stream_));
+        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)(tr.npanels + 1), stream_));
         tr.dir = 1;
         VBK_LAUNCH(k_window_tri, gtri, kTriThreads, sm_tri, stream_, tr);
     }

@@ -148,6 +148,15 @@ void show_small_problem(int m, int n, const int* kA, const int* iA, const double
 static int g_itnlim = 200;
 void set_iteration_limit(int itnlim) { g_itnlim = itnlim > 0 ? itnlim : 200; }
 
+// The batch driver (vbk_batch.cu) runs many solves concurrently, one host thread + one stream each:
+// the iteration log of such a solve is suppressed (per thread), everything else is unchanged.
+static thread_local bool t_quiet = false;
+static thread_local int t_last_iterations = 0;
+void set_thread_quiet(bool quiet) { t_quiet = quiet; }
+int last_thread_iterations() { return t_last_iterations; }
+#define VBK_LOG(...) do { if (!t_quiet) std::printf(__VA_ARGS__); } while (0)
+#define VBK_LOG_FLUSH() do { if (!t_quiet) std::fflush(stdout); } while (0)
+
 void set_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x)
 {
     g_cap.iter = iter; g_cap.E = E; g_cap.D = D; g_cap.ry = rhs_y; g_cap.rx = rhs_x; g_cap.sy = sol_y; g_cap.sx = sol_x;
@@ -164,18 +173,18 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
     cudaStream_t st = W.st;
     int status = 5;
 
-    if (m < 20 && n < 20) show_small_problem(m, n, kA, iA, A, b, c);
+    if (m < 20 && n < 20 && !t_quiet) show_small_problem(m, n, kA, iA, A, b, c);
 
     W.fill(W.x, n, 1.0); W.fill(W.z, n, 1.0); W.fill(W.w, m, 1.0); W.fill(W.y, m, 1.0);
     double phi = 1.0, psi = 1.0;
 
-    std::printf("m = %d,n = %d,nz = %d\n", m, n, nz);
-    std::printf(
+    VBK_LOG("m = %d,n = %d,nz = %d\n", m, n, nz);
+    VBK_LOG(
 "--------------------------------------------------------------------------\n"
 "         |           Primal          |            Dual           |       |\n"
 "  Iter   |  Obj Value       Infeas   |  Obj Value       Infeas   |  mu   |\n"
 "- - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - \n");
-    std::fflush(stdout);
+    VBK_LOG_FLUSH();
     if (timed) { cudaStreamSynchronize(st); prof->setup_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); }
 
     int iter;
@@ -193,7 +202,7 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
             if (phi > psi) { status = 0; break; }
             else if (dual_obj < 0.0) { status = 2; break; }
             else if (primal_obj > 0.0) { status = 4; break; }
-            else { std::printf("Trouble in river city \n"); status = 4; break; }
+            else { VBK_LOG("Trouble in river city \n"); status = 4; break; }
         }
 
         // infeasibilities (hsd.c:182-198)
@@ -213,9 +222,9 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
 
         const double gamma = -(1 - delta) * (dual_obj - primal_obj + psi) + psi - delta * mu / phi;
 
-        std::printf("%8d   %14.7e  %8.1e    %14.7e  %8.1e  %8.1e \n",
+        VBK_LOG("%8d   %14.7e  %8.1e    %14.7e  %8.1e  %8.1e \n",
                     iter, primal_obj / phi + f, normr, dual_obj / phi + f, norms, mu);
-        std::fflush(stdout);
+        VBK_LOG_FLUSH();
 
         // step directions (hsd.c:215-238)
         VBK_LAUNCH(k_ratio, W.g(n), kVecThreads, 0, st, n, W.z.p, W.x.p, W.D.p);
@@ -275,6 +284,7 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
     W.launches(2);
     VBK_CHECK_LAUNCH();
     W.finish(x, y);
+    t_last_iterations = iter;
     if (timed) {
         prof->iterations = iter;
         prof->total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
@@ -291,19 +301,19 @@ int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, cons
     cudaStream_t st = W.st;
     int status = 5;
 
-    if (m < 20 && n < 20) show_small_problem(m, n, kA, iA, A, b, c);
+    if (m < 20 && n < 20 && !t_quiet) show_small_problem(m, n, kA, iA, A, b, c);
 
     W.fill(W.x, n, 1000.0); W.fill(W.z, n, 1000.0); W.fill(W.w, m, 1000.0); W.fill(W.y, m, 1000.0);
     const double delta = 0.02, r = 0.9;
     double normr0 = HUGE_VAL, norms0 = HUGE_VAL;
 
-    std::printf("m = %d,n = %d,nz = %d\n", m, n, nz);
-    std::printf(
+    VBK_LOG("m = %d,n = %d,nz = %d\n", m, n, nz);
+    VBK_LOG(
 "------------------------------------------------------------------\n"
 "         |           Primal          |            Dual           |\n"
 "  Iter   |  Obj Value       Infeas   |  Obj Value       Infeas   |\n"
 "- - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - - \n");
-    std::fflush(stdout);
+    VBK_LOG_FLUSH();
     if (timed) { cudaStreamSynchronize(st); prof->setup_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); }
 
     int iter;
@@ -325,8 +335,8 @@ int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, cons
         const double gamma = d[2] + d[3];                    // intpt.c:155
         const float primal_obj = d[4] + f;
         const float dual_obj = d[5] + f;
-        std::printf("%8d   %14.7e  %8.1e    %14.7e  %8.1e \n", iter, primal_obj, normr, dual_obj, norms);
-        std::fflush(stdout);
+        VBK_LOG("%8d   %14.7e  %8.1e    %14.7e  %8.1e \n", iter, primal_obj, normr, dual_obj, norms);
+        VBK_LOG_FLUSH();
 
         if (normr < 1.0e-6 && norms < 1.0e-6 && gamma < 1.0e-6) { status = 0; break; }   // intpt.c:171-182
         if (normr > 10 * normr0) { status = 2; break; }
@@ -366,6 +376,7 @@ int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, cons
     }
     VBK_CHECK_LAUNCH();
     W.finish(x, y);
+    t_last_iterations = iter;
     if (timed) {
         prof->iterations = iter;
         prof->total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();

@@ -24,6 +24,11 @@ int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, cons
 // lower it (e.g. to stop right after a captured iteration).  <= 0 restores 200.
 void set_iteration_limit(int itnlim);
 
+// per-thread: suppress the iteration log of solver_* calls made by this thread (batch driver);
+// iteration count of the last solver_* call made by this thread
+void set_thread_quiet(bool quiet);
+int last_thread_iterations();
+
 void set_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x);
 
 }  // namespace vbk

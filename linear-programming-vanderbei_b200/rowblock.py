@@ -1,0 +1,160 @@
+"""Row-block partitioned ``smx`` / ``dotprod`` / ``maxv`` over 2/4/8 GPUs (BASELINE.json config 5,
+SURVEY.md 8e).
+
+One process per GPU.  Vectors on the constraint side (length m: rho, w, y, dy, ...) are split into equal
+contiguous row blocks, vectors on the variable side (length n: sigma, z, x, dx, ...) into equal contiguous
+column blocks (the last block is zero-padded so that every rank holds ``ceil(len / world)`` entries and
+the all-gather is a single contiguous collective).
+
+* ``A_x``   (reference ``smx(m, n, A, kA, iA, x, rho)``, src/ipo/hsd.c:182): all-gather x (NCCL over NVLink),
+  then the rank's row block of A -- a slice of the transpose arrays ``atnum`` built (hsd.c:111) -- times
+  the full x with ``vbk_spmv_rows_dev``.  Every output entry is one row sum in ascending column order:
+  bit-identical to the reference's scatter loop (linalg.c:62-70) for any number of ranks.
+* ``At_y``  (``smx(n, m, At, kAt, iAt, y, sigma)``, hsd.c:191): same with the column block of A.
+* ``dots`` / ``absmax`` (``dotprod`` linalg.c:17-25, ``maxv`` linalg.c:108-116): up to 8 local partial
+  reductions in one launch, then ONE all-reduce of those few doubles (SUM, resp. MAX).
+
+The device kernels are csrc/vbk_rowblock.cu; torch is only the carrier of device memory, the stream and
+the collectives.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+_ip = C.POINTER(C.c_int)
+_dp = C.POINTER(C.c_double)
+
+
+def declare(lib):
+    lib.vbk_spmv_rows_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vbk_spmv_rows_dev.restype = None
+    lib.vbk_dots_partial_dev.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vbk_dots_partial_dev.restype = None
+    lib.vbk_absmax_partial_dev.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p]
+    lib.vbk_absmax_partial_dev.restype = None
+    lib.vbk_reduce_scratch_doubles.restype = C.c_int
+    return lib
+
+
+def block_bounds(length: int, rank: int, world: int):
+    """(block size shared by all ranks, first index, one-past-last index) of rank's contiguous block."""
+    per = (length + world - 1) // world
+    lo = min(length, rank * per)
+    return per, lo, min(length, lo + per)
+
+
+class RowBlockOps:
+    """The rank-local half of the partitioned linear algebra of one LP (solver-space A: m x n, CSC
+    ``kA, iA, A`` with its transpose ``kAt, iAt, At`` as ``atnum`` produces it)."""
+
+    def __init__(self, lib, m, n, kA, iA, A, kAt, iAt, At, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.lib, self.group = torch, dist, declare(lib), group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.device = torch.device(device)
+        self.m, self.n = m, n
+        self.rows_per, self.r0, self.r1 = block_bounds(m, self.rank, self.world)
+        self.cols_per, self.c0, self.c1 = block_bounds(n, self.rank, self.world)
+        kA, iA, A = np.asarray(kA), np.asarray(iA), np.asarray(A)
+        kAt, iAt, At = np.asarray(kAt), np.asarray(iAt), np.asarray(At)
+
+        def slab(ptr, idx, val, lo, hi):
+            a, b = int(ptr[lo]), int(ptr[hi])
+            t = lambda v, dt: torch.from_numpy(np.ascontiguousarray(v, dtype=dt)).to(self.device)
+            return (t(ptr[lo:hi + 1] - ptr[lo], np.int32), t(idx[a:b] if b > a else np.zeros(1), np.int32),
+                    t(val[a:b] if b > a else np.zeros(1), np.float64), b - a)
+        # rows r0..r1 of A  = columns r0..r1 of the CSC transpose;  columns c0..c1 of A = rows of A^T
+        self.rowblk = slab(kAt, iAt, At, self.r0, self.r1)
+        self.colblk = slab(kA, iA, A, self.c0, self.c1)
+        self.full_x = torch.zeros(self.cols_per * self.world, dtype=torch.float64, device=self.device)
+        self.full_y = torch.zeros(self.rows_per * self.world, dtype=torch.float64, device=self.device)
+        self.scratch = torch.zeros(int(self.lib.vbk_reduce_scratch_doubles()), dtype=torch.float64, device=self.device)
+        self.red = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.launches = 0
+
+    # -- partition helpers -------------------------------------------------------------------------
+    def local_x(self, full):
+        """This rank's (zero-padded) block of a length-n host vector."""
+        v = np.zeros(self.cols_per)
+        v[: self.c1 - self.c0] = np.asarray(full)[self.c0:self.c1]
+        return self.torch.from_numpy(v).to(self.device)
+
+    def local_y(self, full):
+        v = np.zeros(self.rows_per)
+        v[: self.r1 - self.r0] = np.asarray(full)[self.r0:self.r1]
+        return self.torch.from_numpy(v).to(self.device)
+
+    def _stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        return None
+
+    def _gather(self, full, local):
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(full, local, group=self.group)
+        else:
+            full.copy_(local)
+        return full
+
+    # -- smx -----------------------------------------------------------------------------------------
+    def A_x(self, x_local, out=None):
+        """rho[rows of this rank] = (A x)[rows]; x_local is this rank's block of x."""
+        out = out if out is not None else self.torch.zeros(self.rows_per, dtype=self.torch.float64, device=self.device)
+        full = self._gather(self.full_x, x_local)
+        ptr, idx, val, _ = self.rowblk
+        self.lib.vbk_spmv_rows_dev(self.r1 - self.r0, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(),
+                                   full.data_ptr(), out.data_ptr(), self._stream())
+        self.launches += 1
+        return out
+
+    def At_y(self, y_local, out=None):
+        """sigma[cols of this rank] = (A^T y)[cols]; y_local is this rank's block of y."""
+        out = out if out is not None else self.torch.zeros(self.cols_per, dtype=self.torch.float64, device=self.device)
+        full = self._gather(self.full_y, y_local)
+        ptr, idx, val, _ = self.colblk
+        self.lib.vbk_spmv_rows_dev(self.c1 - self.c0, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(),
+                                   full.data_ptr(), out.data_ptr(), self._stream())
+        self.launches += 1
+        return out
+
+    # -- dotprod / maxv --------------------------------------------------------------------------
+    def _ptrs(self, vecs):
+        arr = (C.c_void_p * len(vecs))(*[v.data_ptr() for v in vecs])
+        lens = (C.c_longlong * len(vecs))(*[int(v.numel()) for v in vecs])
+        return arr, lens
+
+    def dots(self, pairs):
+        """Global dot products of up to 8 pairs of partitioned vectors; returns a device tensor [len(pairs)]
+        (every rank gets the same values)."""
+        k = len(pairs)
+        xs, lens = self._ptrs([p[0] for p in pairs])
+        ys, _ = self._ptrs([p[1] for p in pairs])
+        out = self.red[:k]
+        self.lib.vbk_dots_partial_dev(k, xs, ys, lens, out.data_ptr(), self.scratch.data_ptr(), self._stream())
+        self.launches += 2
+        if self.world > 1:
+            self.dist.all_reduce(out, op=self.dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def absmax(self, vecs):
+        """Global max-norms (maxv) of up to 8 partitioned vectors; device tensor [len(vecs)]."""
+        k = len(vecs)
+        xs, lens = self._ptrs(vecs)
+        out = self.red[:k]
+        self.lib.vbk_absmax_partial_dev(k, xs, lens, out.data_ptr(), self._stream())
+        self.launches += 1
+        if self.world > 1:
+            self.dist.all_reduce(out, op=self.dist.ReduceOp.MAX, group=self.group)
+        return out
+
+    # -- algorithmic bytes of one A_x + At_y pair on this rank (SURVEY.md 8d work model) ----------------
+    def spmv_bytes(self):
+        nz_r, nz_c = self.rowblk[3], self.colblk[3]
+        rows, cols = self.r1 - self.r0, self.c1 - self.c0
+        return (12 * nz_r + 4 * (rows + 1) + 8 * self.n + 8 * rows) + (12 * nz_c + 4 * (cols + 1) + 8 * self.m + 8 * cols)

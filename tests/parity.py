@@ -113,11 +113,11 @@ def check_kkt_step_fast(vbkkt, lib, oracle, lp, method, it, tol=1e-6):
         K.close()
 
 
-def check_full_solve_fast(vbkkt, lib, lp, method="hsd"):
+def check_full_solve_fast(vbkkt, lib, lp, method="hsd", iter_slack=1):
     """FAST mode end to end on a problem of the robust list: the north_star tolerances
     (status, iteration count +-1, objective 1e-8 relative, infeasibilities 1e-7)."""
     st, log, x, y, _ = H.solve_via(vbkkt, lib, lp, method, mode=vbkkt.MODE_FAST)
-    north_star_tolerances(lp, method, x, y, st, log)
+    north_star_tolerances(lp, method, x, y, st, log, iter_slack=iter_slack)
     return st
 
 
@@ -138,7 +138,7 @@ def check_full_solve(vbkkt, lib, lp, method, want_bits=True):
     return st
 
 
-def north_star_tolerances(lp, method, x, y, status, log):
+def north_star_tolerances(lp, method, x, y, status, log, iter_slack=1):
     """The tolerance form of parity (BASELINE.json north_star): objective 1e-8 relative,
     infeasibilities 1e-7, iteration count +-1, same status."""
     xr, yr = lp.extra[method + "_x"], lp.extra[method + "_y"]
@@ -149,7 +149,7 @@ def north_star_tolerances(lp, method, x, y, status, log):
     assert abs(dobj - dobj_r) <= 1e-8 * max(1.0, abs(dobj_r))
     n_it = len(H.iteration_lines(log))
     n_ref = len(H.iteration_lines(str(lp.extra[method + "_log"])))
-    assert abs(n_it - n_ref) <= 1
+    assert abs(n_it - n_ref) <= iter_slack, (n_it, n_ref)
     import scipy.sparse as sp
     A = sp.csc_matrix((lp.A, lp.iA, lp.kA), shape=(lp.m, lp.n))
     pinf = np.linalg.norm(np.maximum(A @ x - lp.b, 0.0)), np.linalg.norm(np.maximum(A @ xr - lp.b, 0.0))
