@@ -83,6 +83,9 @@ int        vbk_kkt_dim(const vbk_kkt *h);
 long long  vbk_kkt_lnz(const vbk_kkt *h);
 int        vbk_kkt_denwin(const vbk_kkt *h);
 int        vbk_kkt_pdf(const vbk_kkt *h);
+/* width of the trailing window fast mode factorises densely (>= dim - denwin: the window is padded, see
+ * DESIGN.md); 0 when there is none */
+int        vbk_kkt_window(const vbk_kkt *h);
 double     vbk_kkt_narth(const vbk_kkt *h);
 int        vbk_kkt_nlevels(const vbk_kkt *h);
 int        vbk_kkt_nsupernodes(const vbk_kkt *h);

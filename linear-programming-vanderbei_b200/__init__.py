@@ -95,7 +95,7 @@ def _declare(lib):
     lib.vbk_kkt_sync.argtypes = [C.c_void_p]
     lib.vbk_kkt_stream.argtypes = [C.c_void_p]
     lib.vbk_kkt_stream.restype = C.c_void_p
-    for name, rt in [("dim", C.c_int), ("lnz", C.c_longlong), ("denwin", C.c_int), ("pdf", C.c_int),
+    for name, rt in [("dim", C.c_int), ("lnz", C.c_longlong), ("denwin", C.c_int), ("pdf", C.c_int), ("window", C.c_int),
                      ("narth", C.c_double), ("nlevels", C.c_int), ("nsupernodes", C.c_int),
                      ("perm", _ip), ("iperm", _ip), ("kAAt", _ip), ("iAAt", _ip),
                      ("epsdiag", C.c_double), ("ndep", C.c_int), ("last_passes", C.c_int),
@@ -229,6 +229,8 @@ class KKT:
     def denwin(self): return int(self.lib.vbk_kkt_denwin(self.h))
     @property
     def pdf(self): return int(self.lib.vbk_kkt_pdf(self.h))
+    @property
+    def window(self): return int(self.lib.vbk_kkt_window(self.h))
     @property
     def narth(self): return float(self.lib.vbk_kkt_narth(self.h))
     @property

@@ -13,10 +13,41 @@
 
 #include <atomic>
 #include <chrono>
+#include <csignal>
+#include <cstdlib>
+#include <execinfo.h>
+#include <unistd.h>
 #include <thread>
 #include <vector>
 
 using namespace vbk;
+
+namespace {
+// $VBK_SEGV_TRACE (debugging aid): raw backtrace of the faulting thread on stderr, then the default action.
+// Runs on an alternate stack so that a stack overflow is reported too.
+void segv_trace(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, n, 2);
+    std::signal(sig, SIG_DFL);
+    raise(sig);
+}
+void install_segv_trace()
+{
+    if (!std::getenv("VBK_SEGV_TRACE")) return;
+    void* warm[4];
+    backtrace(warm, 4);                      // loads libgcc now, not inside the handler
+    stack_t ss;
+    ss.ss_sp = std::malloc(1 << 16); ss.ss_size = 1 << 16; ss.ss_flags = 0;
+    sigaltstack(&ss, nullptr);
+    struct sigaction sa;
+    sa.sa_handler = segv_trace; sigemptyset(&sa.sa_mask); sa.sa_flags = SA_ONSTACK;
+    sigaction(SIGSEGV, &sa, nullptr);
+    sigaction(SIGBUS, &sa, nullptr);
+    sigaction(SIGABRT, &sa, nullptr);
+}
+}  // namespace
 
 extern "C" int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp_desc* lps, int nstreams)
 {
@@ -28,6 +59,7 @@ extern "C" int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp
 #ifndef VBK_EMU
         VBK_CUDA(cudaSetDevice(device));
 #endif
+        install_segv_trace();
         set_thread_quiet(true);
         for (;;) {
             const int i = next.fetch_add(1);

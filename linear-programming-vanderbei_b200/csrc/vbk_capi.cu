@@ -203,6 +203,7 @@ int vbk_kkt_dim(const vbk_kkt* h) { return h->impl.sym().N; }
 long long vbk_kkt_lnz(const vbk_kkt* h) { return h->impl.sym().lnz(); }
 int vbk_kkt_denwin(const vbk_kkt* h) { return h->impl.sym().denwin; }
 int vbk_kkt_pdf(const vbk_kkt* h) { return h->impl.sym().pdf; }
+int vbk_kkt_window(const vbk_kkt* h) { return h->impl.sym().N - h->impl.sym().dense_start; }
 double vbk_kkt_narth(const vbk_kkt* h) { return h->impl.sym().narth; }
 int vbk_kkt_nlevels(const vbk_kkt* h) { return h->impl.sym().nlevels; }
 int vbk_kkt_nsupernodes(const vbk_kkt* h) { return (int)h->impl.sym().sn_ptr.size() - 1; }

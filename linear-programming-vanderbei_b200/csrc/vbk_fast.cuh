@@ -37,6 +37,11 @@ struct DenseArgs {
     const int* perm; int T, n_ld;
     int* counters;
     double tol;
+    // scale of the substitute for a dependent pivot: reference rule sgn*1e-8 (ldlt.c:612) when 0, otherwise
+    // sgn*max(1e-8, piv_scale * largest term magnitude) ("static pivoting")
+    double piv_scale;
+    unsigned long long* prof;  // $VBK_PROF: cycle counters of the panel kernels (16 slots), else nullptr
+    double* PB;                // packed panel buffer (vbk_fast3.cuh): L11^T, reciprocal pivots, keep flags
     // two-level blocking (vbk_fast2.cuh): the rank-k update takes its k columns S[:, kcol0..kcol0+klen)
     // and P[:, pcol0..pcol0+klen) and touches target rows/columns [rbase, W) x [rbase, cmax)
     int kcol0, klen, pcol0, rbase, cmax;

@@ -72,7 +72,11 @@ static __global__ void __launch_bounds__(32) k_dense_diag_w(DenseArgs a)
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) { double o = __shfl_xor_sync(0xffffffffu, mymax, s); if (o > mymax) mymax = o; }
                 if (mymax < 1.0e+6 * 1.0e-8) keep = 0;
-                else d = (a.perm[a.T + p + c] < a.n_ld ? -1 : 1) * 1.0e-8;
+                else {
+                    double sub = a.piv_scale * magc;
+                    if (!(sub > 1.0e-8)) sub = 1.0e-8;
+                    d = (a.perm[a.T + p + c] < a.n_ld ? -1 : 1) * sub;
+                }
                 if (lane == 0) atomicAdd(&a.counters[C_NDEP], 1);
             }
             if (lane == c) { myd = d; mykeep = keep; row[c] = d; sd[c] = d; skeep[c] = keep; }

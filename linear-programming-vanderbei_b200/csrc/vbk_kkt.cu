@@ -50,6 +50,7 @@ Kkt::Kkt(int device, int mode) : device_(device), mode_(mode)
     cudaDeviceProp prop;
     VBK_CUDA(cudaGetDeviceProperties(&prop, device_));
     num_sms_ = prop.multiProcessorCount;
+    smem_optin_ = (int)prop.sharedMemPerBlockOptin;
     VBK_CUDA(cudaStreamCreate(&stream_));
     VBK_CUDA(cudaMallocHost((void**)&pin_bits_, sizeof(unsigned long long) * S_COUNT));
     VBK_CUDA(cudaMallocHost((void**)&pin_scal_, sizeof(double) * S_COUNT));
@@ -178,7 +179,9 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
         tiled_smem_ = sizeof(double) * ((size_t)tile_doubles_ + temp_cap_ + 2 * kTileMaxBatch + kTiledThreads + 2) +
                       sizeof(int) * ((size_t)2 * kTileMaxBatch + 1 + sym_.rowblk + 8);
 #ifndef VBK_EMU
-        VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_));
+        // the cap is per FUNCTION, not per handle: concurrent handles (batch driver) need different sizes, so the
+        // cap is always raised to the device maximum and never lowered
+        VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
 #endif
         int occ2 = 1;
         VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_factor_tiled, kTiledThreads, tiled_smem_));

@@ -102,6 +102,7 @@ private:
     int device_, mode_;
     bool debug_ = false;   // $VBK_DEBUG: trace refinement passes on stderr
     int num_sms_ = 1;
+    int smem_optin_ = 48 << 10;   // largest dynamic shared memory a CTA may opt in to on this device
     cudaStream_t stream_ = 0;
     bool analyzed_ = false;
     Symbolic sym_;
@@ -142,8 +143,9 @@ private:
     // fast mode (vbk_fast.cuh, vbk_kkt_fast.cu): dense scratch for the trailing window
     bool fast_ready_ = false, light_schur_ = false;
     int panel_nb_ = 32;
-    DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_;
+    DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_, panel_buf_;
     DevArray<int> wmark_, pan_keep_, tri_flags_;
+    DevArray<unsigned long long> panel_prof_;
     void prepare_fast();
     void factor_window_fast(TiledArgs& ta);
     void rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_smem);

@@ -1,6 +1,6 @@
 // vbk_kkt_fast.cu -- host orchestration of FAST mode (kernels in vbk_fast.cuh).
 #include "vbk_kkt.h"
-#include "vbk_fast2.cuh"
+#include "vbk_fast3.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -19,7 +19,7 @@ void Kkt::prepare_fast()
     Sw_.alloc((size_t)W * W);
     P_.alloc((size_t)W * kOuterPanel);
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
-    pan_d_.alloc(kPanelMax); pan_keep_.alloc(kPanelMax);
+    pan_d_.alloc(kPanelW); pan_keep_.alloc(kPanelW); panel_buf_.alloc(kPanelBufDoubles);
     tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
     {
         // how many sparse-column contributions do the window rows see?  Few => light Schur kernel.
@@ -34,11 +34,13 @@ void Kkt::prepare_fast()
     }
 #ifndef VBK_EMU
     // kernels are `static` in the headers: this translation unit launches its own copy
-    VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_));
+    VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_rt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
+    VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_panel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsSmem));
 #endif
     fast_ready_ = true;
 }
@@ -73,13 +75,20 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     // 3. blocked right-looking dense LDL^T of the window
     DenseArgs da;
     da.W = W; da.ld = W; da.S = Sw_.p; da.P = P_.p; da.dvec = dvec_.p; da.wmag = wmag_.p; da.wmark = wmark_.p;
-    da.pan_d = pan_d_.p; da.pan_keep = pan_keep_.p; da.perm = perm_.p; da.T = T; da.n_ld = sym_.n;
+    da.pan_d = pan_d_.p; da.pan_keep = pan_keep_.p; da.PB = panel_buf_.p; da.prof = nullptr; da.perm = perm_.p; da.T = T; da.n_ld = sym_.n;
     da.counters = counters_.p;
     // The reference's "exactly zero" pivots come from absorption: a term T swallows the running value
     // (|value| < ulp(T)/2) and is then cancelled exactly.  With re-associated sums the same pivot comes
     // out as the tiny true value instead, so the test is |d| <= 2^-52 * (largest term magnitude).
     da.tol = 2.220446049250313e-16;
     if (const char* e = std::getenv("VBK_PIVOT_TOL_ULPS")) da.tol *= std::max(0.0, std::atof(e));
+    // A window pivot that fails the test above is rounding noise of terms of magnitude wmag.  The reference
+    // substitutes sgn*1e-8 whatever the scale (ldlt.c:612); with noise-level pivots flagged too, that choice
+    // multiplies the column by up to 1e8*wmag and overflowed on the random m=2000 LPs of BASELINE config 4
+    // (profiles/r01_summary.md).  Fast mode substitutes sgn*max(1e-8, sqrt(eps)*wmag) instead ("static
+    // pivoting"; iterative refinement absorbs the perturbation).  $VBK_PIVOT_STATIC=0 restores the literal rule.
+    da.piv_scale = 1.4901161193847656e-08;
+    if (const char* e = std::getenv("VBK_PIVOT_STATIC")) da.piv_scale = std::atof(e);
     const size_t sm_diag = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax + kDenseThreads) + sizeof(int) * kPanelMax;
     const size_t sm_trsm = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;
     const size_t sm_upd = sizeof(double) * 2 * kPanelMax * kTileDim;
@@ -89,7 +98,38 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     int launches = 2;
     const char* ed = std::getenv("VBK_DENSE");
     const bool dense_v1 = ed && std::string(ed) == "v1";
-    if (!dense_v1) {
+    const bool dense_v2 = ed && std::string(ed) == "v2";
+    if (!dense_v1 && !dense_v2) {
+        // 128-column panels (vbk_fast3.cuh): diagonal block, rows below, rank-128 trailing update
+        static const bool prof_on = std::getenv("VBK_PROF") != nullptr;
+        if (prof_on) {
+            panel_prof_.alloc(16);
+            VBK_CUDA(cudaMemsetAsync(panel_prof_.p, 0, 16 * sizeof(unsigned long long), stream_));
+            da.prof = panel_prof_.p;
+        }
+        for (int P0 = 0; P0 < W; P0 += kPanelW) {
+            da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0;
+            VBK_LAUNCH(k_panel_diag, 1, kDiagThreads, kPanelDiagSmem, stream_, da);
+            ++launches;
+            const int below = W - P0 - da.nb;
+            if (below <= 0) continue;
+            const int g = std::min((below + kRowsPerCta - 1) / kRowsPerCta, num_sms_ * 4);
+            VBK_LAUNCH(k_panel_rows, g, kRowThreads, kPanelRowsSmem, stream_, da);
+            da.kcol0 = P0; da.klen = da.nb; da.rbase = P0 + da.nb; da.cmax = W;
+            const int tiles = (below + kUpdTD - 1) / kUpdTD;
+            VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
+            launches += 2;
+        }
+    }
+    if (da.prof) {
+        unsigned long long h[16];
+        panel_prof_.download(h, 16, stream_);
+        VBK_CUDA(cudaStreamSynchronize(stream_));
+        std::fprintf(stderr, "vbkkt panel profile (cycles of thread 0, CTA 0, summed over %d panels): diag load %llu, warp LDL %llu, "
+                     "block trsm %llu, block update %llu, store %llu | rows: panel fetch %llu, row loads %llu, rank update %llu, "
+                     "stages %llu, stores %llu\n", (W + kPanelW - 1) / kPanelW, h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
+    }
+    if (dense_v2) {
         // two-level blocking (vbk_fast2.cuh): inner panels of panel_nb_ columns, one rank-(outer) update of
         // the trailing matrix per outer panel
         const size_t sm_diag_w = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;

@@ -86,20 +86,10 @@ def test_fast_mode_kkt_step(vbkkt, gpu_lib, oracle_lib, name, it):
     P.check_kkt_step_fast(vbkkt, gpu_lib, oracle_lib, H.load_fixture(name), "hsd", it)
 
 
-@pytest.mark.parametrize("name", ["afiro", "adlittle", "israel", "sc205", "fit1d", "ship04l", "scsd1", "25fv47"])
+@pytest.mark.parametrize("name", ["afiro", "adlittle", "blend", "israel", "sc205", "fit1d", "ship04l", "scsd1", "25fv47"])
 def test_fast_mode_full_solve_north_star_tolerances(vbkkt, gpu_lib, name):
     """Robust-list problems solved in fast mode: status, iterations +-1, objective 1e-8."""
     P.check_full_solve_fast(vbkkt, gpu_lib, H.load_fixture(name))
-
-
-def test_fast_mode_blend_is_one_predictor_corrector_pair_off(vbkkt, gpu_lib):
-    """The documented limit of fast mode: inside the dense window the reference's
-    "pivot is EXACTLY zero" rule (ldlt.c:600-614) can only be applied by tolerance, because an exact zero
-    and rounding noise are indistinguishable once the sums are re-associated.  On blend's last, nearly
-    singular iterations that flags more dependent rows than the reference does and the run needs one more
-    predictor/corrector pair (35 lines for 33); status, objective (1e-8) and infeasibilities (1e-7) still
-    hold.  Strict mode reproduces the 33 lines byte for byte (FULL_HSD above)."""
-    P.check_full_solve_fast(vbkkt, gpu_lib, H.load_fixture("blend"), iter_slack=2)
 
 
 def test_strict_mode_big_iterates_bit_equal(vbkkt, gpu_lib):
