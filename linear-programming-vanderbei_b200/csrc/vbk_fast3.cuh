@@ -48,6 +48,15 @@ constexpr size_t kPanelDiagSmem = sizeof(double) * (kPanelW * kLDD + (kPanelW - 
                                   + sizeof(int) * (kPanelW + 4);
 constexpr size_t kPanelRowsSmem = sizeof(double) * (kPanelBufDoubles + (kPanelW - 32) * kRowsPerCta) + 16;
 
+// correctly rounded reciprocal: one MUFU seed + Newton steps, about half the dependent chain of a full division
+__device__ __forceinline__ double vbk_rcp(double d) {
+#ifdef VBK_EMU
+    return 1.0 / d;
+#else
+    return __drcp_rn(d);
+#endif
+}
+
 // $VBK_PROF: thread 0 of CTA 0 adds the cycles since *t to slot and restarts the clock
 __device__ __forceinline__ void panel_tick(const DenseArgs& a, int slot, long long* t)
 {
@@ -176,16 +185,33 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
                 }
                 if (tid == 0) atomicAdd(&a.counters[C_NDEP], 1);
             }
-            const double inv = keep ? 1.0 / d : 0.0;
+            const double inv = keep ? vbk_rcp(d) : 0.0;
             if (tid == 0) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
             const int c2 = lane;
             if (c2 > c && c2 < nbb) {
                 const double ac2 = blk[(b0 + c2) * kLDD + b0 + c] * inv;        // l_{c2,c}
-                for (int r = warp; r < nbb; r += (nt >> 5)) {                   // warp w: rows w, w + nwarps, ...
-                    if (r < c2) continue;
-                    const double upd = blk[(b0 + r) * kLDD + b0 + c] * ac2;     // a_{r,c} * l_{c2,c} = l d l
-                    blk[(b0 + r) * kLDD + b0 + c2] -= upd;
+                // warp w owns rows w, w + nwarps, ...: all loads first, then the arithmetic, then the stores (a
+                // load-update-store loop is serialised by the compiler: the store may alias the next load)
+                constexpr int kRpw = 32 / (kDiagThreads / 32);
+                double ar[kRpw], tv[kRpw];
+#pragma unroll
+                for (int i = 0; i < kRpw; ++i) {
+                    const int r = warp + i * (kDiagThreads / 32);
+                    const bool on = r >= c2 && r < nbb;
+                    ar[i] = on ? blk[(b0 + r) * kLDD + b0 + c] : 0.0;           // a_{r,c}
+                    tv[i] = on ? blk[(b0 + r) * kLDD + b0 + c2] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < kRpw; ++i) {
+                    const int r = warp + i * (kDiagThreads / 32);
+                    const double upd = ar[i] * ac2;                             // a_{r,c} * l_{c2,c} = l d l
+                    tv[i] -= upd;
                     if (r == c2 && fabs(upd) > wm[b0 + r]) wm[b0 + r] = fabs(upd);
+                }
+#pragma unroll
+                for (int i = 0; i < kRpw; ++i) {
+                    const int r = warp + i * (kDiagThreads / 32);
+                    if (r >= c2 && r < nbb) blk[(b0 + r) * kLDD + b0 + c2] = tv[i];
                 }
             }
         }
@@ -400,6 +426,63 @@ static __global__ void __launch_bounds__(kRowThreads) k_panel_rows(DenseArgs a)
             if (dabs > a.wmag[r]) a.wmag[r] = dabs;
         }
         __syncwarp();
+    }
+}
+
+// Look-ahead "A part": rank-klen update of the column strip [rbase, cmax) (at most kPanelW columns: the NEXT panel)
+// for all rows >= rbase.  It sits on the critical path between two panel factorisations, so it is cut into many
+// small CTAs -- 64 x 64 tiles, 256 threads, 4 x 4 register micro-tiles (2048 FMAs per thread) -- instead of the
+// 128 x 128 / 8 x 8 tiles of k_dense_update_k (8192 FMAs per thread, ~60 us for a grid that is too small to fill
+// the GPU anyway).
+#ifdef VBK_EMU
+constexpr int kStripTG = 4;
+#else
+constexpr int kStripTG = 16;
+#endif
+constexpr int kStripTD = 4 * kStripTG;
+constexpr int kStripThreads = kStripTG * kStripTG;
+static __global__ void __launch_bounds__(kStripThreads) k_dense_update_strip(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* As = reinterpret_cast<double*>(raw);             // [kPanelMax][kStripTD]
+    double* Bs = As + kPanelMax * kStripTD;
+    const int r0 = a.rbase + blockIdx.y * kStripTD, c0 = a.rbase + blockIdx.x * kStripTD;
+    if (r0 + kStripTD <= c0 || c0 >= a.cmax) return;
+    const int tid = threadIdx.x, tx = tid % kStripTG, ty = tid / kStripTG;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (int kc = 0; kc < a.klen; kc += kPanelMax) {
+        const int kn = (a.klen - kc < kPanelMax) ? (a.klen - kc) : kPanelMax;
+        __syncthreads();
+        for (int e = tid; e < kPanelMax * kStripTD; e += kStripThreads) {
+            const int x = e % kStripTD, c = e / kStripTD;
+            As[c * kStripTD + x] = (c < kn && r0 + x < a.W) ? SW(a, r0 + x, a.kcol0 + kc + c) : 0.0;
+            Bs[c * kStripTD + x] = (c < kn && c0 + x < a.W) ? a.P[(size_t)(c0 + x) + (size_t)(a.pcol0 + kc + c) * a.W] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < kPanelMax; ++c) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { av[u] = As[c * kStripTD + tx + kStripTG * u]; bv[u] = Bs[c * kStripTD + ty + kStripTG * u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int c2 = c0 + ty + kStripTG * v;
+        if (c2 >= a.W || c2 >= a.cmax) continue;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + tx + kStripTG * u;
+            if (r < a.W && r > c2) SW(a, r, c2) -= acc[u][v];
+        }
     }
 }
 

@@ -69,7 +69,12 @@ Kkt::~Kkt()
     if (pin_cnt_) cudaFreeHost(pin_cnt_);
     if (ev_f0_) cudaEventDestroy(ev_f0_);
     if (ev_f1_) cudaEventDestroy(ev_f1_);
+    for (int u = 0; u < 2; ++u) {
+        if (ev_rows_[u]) cudaEventDestroy(ev_rows_[u]);
+        if (ev_updb_[u]) cudaEventDestroy(ev_updb_[u]);
+    }
 #ifndef VBK_EMU
+    if (stream2_) cudaStreamDestroy(stream2_);
     if (stream_) cudaStreamDestroy(stream_);
 #endif
 }

@@ -146,6 +146,9 @@ private:
     DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_, panel_buf_;
     DevArray<int> wmark_, pan_keep_, tri_flags_;
     DevArray<unsigned long long> panel_prof_;
+    // look-ahead: the bulk of a panel's trailing update runs on a second stream while the next panel is factorised
+    cudaStream_t stream2_ = 0;
+    cudaEvent_t ev_rows_[2] = {nullptr, nullptr}, ev_updb_[2] = {nullptr, nullptr};
     void prepare_fast();
     void factor_window_fast(TiledArgs& ta);
     void rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_smem);

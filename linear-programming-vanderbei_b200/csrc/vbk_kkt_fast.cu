@@ -17,7 +17,7 @@ void Kkt::prepare_fast()
     if (const char* e = std::getenv("VBK_PANEL")) panel_nb_ = std::max(1, std::min(kPanelMax, std::atoi(e)));
     else panel_nb_ = kPanelMax;
     Sw_.alloc((size_t)W * W);
-    P_.alloc((size_t)W * kOuterPanel);
+    P_.alloc((size_t)2 * W * kOuterPanel);          // two panels of L21*D: the look-ahead keeps two updates in flight
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
     pan_d_.alloc(kPanelW); pan_keep_.alloc(kPanelW); panel_buf_.alloc(kPanelBufDoubles);
     tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
@@ -41,6 +41,15 @@ void Kkt::prepare_fast()
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsSmem));
+#endif
+#ifndef VBK_EMU
+    if (!stream2_) {
+        VBK_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+        for (int u = 0; u < 2; ++u) {
+            VBK_CUDA(cudaEventCreateWithFlags(&ev_rows_[u], cudaEventDisableTiming));
+            VBK_CUDA(cudaEventCreateWithFlags(&ev_updb_[u], cudaEventDisableTiming));
+        }
+    }
 #endif
     fast_ready_ = true;
 }
@@ -107,19 +116,68 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             VBK_CUDA(cudaMemsetAsync(panel_prof_.p, 0, 16 * sizeof(unsigned long long), stream_));
             da.prof = panel_prof_.p;
         }
-        for (int P0 = 0; P0 < W; P0 += kPanelW) {
+        const char* el = std::getenv("VBK_LOOKAHEAD");
+#ifdef VBK_EMU
+        const bool lookahead = !(el && el[0] == '0');             // same split of the update, one (emulated) stream
+        cudaStream_t sB = stream_;
+#else
+        const bool lookahead = !(el && el[0] == '0') && stream2_ != nullptr;
+        cudaStream_t sB = stream2_;
+#endif
+        // Look-ahead of depth one.  Panel k's rank-128 update is split: the columns of panel k+1 ("A part", few
+        // tiles) stay on the main stream, everything to the right of them ("B part", nearly all the flops) goes to
+        // a second stream and overlaps with the factorisation of panel k+1, which is a latency-bound chain on one or
+        // a few SMs.  Hazards: B_k reads P_k and the columns of panel k and writes strictly-lower entries right of
+        // panel k+1 only -- nothing panel k+1's kernels touch (they write their own columns, the other P buffer and
+        // diagonal entries); A_{k+1} and rows_{k+2} (which reuses P_k's buffer) wait for B_k.
+        int k = 0, last_b = -1;
+        for (int P0 = 0; P0 < W; P0 += kPanelW, ++k) {
             da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0;
+            da.P = P_.p + (size_t)(lookahead ? (k & 1) : 0) * W * kOuterPanel;
             VBK_LAUNCH(k_panel_diag, 1, kDiagThreads, kPanelDiagSmem, stream_, da);
             ++launches;
             const int below = W - P0 - da.nb;
             if (below <= 0) continue;
             const int g = std::min((below + kRowsPerCta - 1) / kRowsPerCta, num_sms_ * 4);
             VBK_LAUNCH(k_panel_rows, g, kRowThreads, kPanelRowsSmem, stream_, da);
-            da.kcol0 = P0; da.klen = da.nb; da.rbase = P0 + da.nb; da.cmax = W;
-            const int tiles = (below + kUpdTD - 1) / kUpdTD;
-            VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
-            launches += 2;
+            ++launches;
+            const int kend = P0 + da.nb;
+            da.kcol0 = P0; da.klen = da.nb;
+            if (!lookahead) {
+                da.rbase = kend; da.cmax = W;
+                const int tiles = (below + kUpdTD - 1) / kUpdTD;
+                VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
+                ++launches;
+                continue;
+            }
+            const int rest = W - (kend + kPanelW);                  // columns right of panel k+1
+            if (rest > 0) {                                         // B part on the second stream
+#ifndef VBK_EMU
+                VBK_CUDA(cudaEventRecord(ev_rows_[k & 1], stream_));
+                VBK_CUDA(cudaStreamWaitEvent(sB, ev_rows_[k & 1], 0));
+#endif
+                DenseArgs db = da;
+                db.rbase = kend + kPanelW; db.cmax = W;
+                const int tiles = (rest + kUpdTD - 1) / kUpdTD;
+                VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, sB, db);
+#ifndef VBK_EMU
+                VBK_CUDA(cudaEventRecord(ev_updb_[k & 1], sB));
+#endif
+                ++launches;
+            }
+            // A part: columns of panel k+1, all rows below panel k.  Those columns were last written by B_{k-1}.
+#ifndef VBK_EMU
+            if (last_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[last_b & 1], 0));
+#endif
+            last_b = rest > 0 ? k : -1;
+            da.rbase = kend; da.cmax = std::min(kend + kPanelW, W);
+            const int tr = (below + kStripTD - 1) / kStripTD, tc = (da.cmax - kend + kStripTD - 1) / kStripTD;
+            VBK_LAUNCH(k_dense_update_strip, dim3(tc, tr), kStripThreads, sizeof(double) * 2 * kPanelMax * kStripTD, stream_, da);
+            ++launches;
         }
+#ifndef VBK_EMU
+        if (lookahead && last_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[last_b & 1], 0));
+#endif
     }
     if (da.prof) {
         unsigned long long h[16];
