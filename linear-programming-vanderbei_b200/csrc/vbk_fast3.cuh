@@ -44,9 +44,34 @@ constexpr int kRowThreads = 4 * kRowsPerCta;
 // packed panel buffer written by k_panel_diag, read by k_panel_rows: L11 transposed (element (row, col) at
 // [col * kLDT + row], zero on and above the diagonal and in the padding), reciprocal pivots, keep flags (0/1)
 constexpr int kPanelBufDoubles = kPanelW * kLDT + 2 * kPanelW;
-constexpr size_t kPanelDiagSmem = sizeof(double) * (kPanelW * kLDD + (kPanelW - 32) * 33 + 3 * kPanelW + kDiagThreads)
+constexpr size_t kPanelDiagSmem = sizeof(double) * (kPanelW * kLDD + (kPanelW - 32) * 33 + 3 * kPanelW + kDiagThreads + 192)
                                   + sizeof(int) * (kPanelW + 4);
 constexpr size_t kPanelRowsSmem = sizeof(double) * (kPanelBufDoubles + (kPanelW - 32) * kRowsPerCta) + 16;
+
+#ifndef VBK_EMU
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool ok)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = ok ? 8 : 0;                  // src-size 0: destination is zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool ok)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// FP64 tensor-path MMA, D(8x8) += A(8x4) B(4x8).  With g = lane / 4, t = lane % 4 a thread holds A[g][t], B[t][g]
+// and C[g][2t], C[g][2t+1] (PTX ISA, mma.m8n8k4 .f64 fragments).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double av, double bv)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+}
+#endif
 
 // correctly rounded reciprocal: one MUFU seed + Newton steps, about half the dependent chain of a full division
 __device__ __forceinline__ double vbk_rcp(double d) {
@@ -54,6 +79,23 @@ __device__ __forceinline__ double vbk_rcp(double d) {
     return 1.0 / d;
 #else
     return __drcp_rn(d);
+#endif
+}
+
+// reciprocal to full double precision without the special-case call of __drcp_rn (that call is a scheduling
+// barrier for the compiler): MUFU seed (relative error ~2^-20), one cubic and one quadratic Newton step.  Pivots
+// outside the normal range do not get here (the dependent-pivot test catches them).
+__device__ __forceinline__ double vbk_rcp_fast(double d) {
+#ifdef VBK_EMU
+    return 1.0 / d;
+#else
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    e = fma(e, e, e);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
 #endif
 }
 
@@ -130,6 +172,35 @@ __device__ double panel_colmax(const DenseArgs& a, int b0, int nbb, int cabs, in
     return mymax;
 }
 
+// Rare path of k_panel_diag, called by all lanes of warp 0 when the pivot of column c of the current sub-block is
+// "zero" (|d| <= tol * largest term, reference rule ldlt.c:600-614): the other warps are released from their
+// command loop to help with max |column| over every row below (panel_colmax), the result decides between dropping
+// the row (returns 0) and substituting the pivot (returns the substitute, never 0).  One copy, out of line: the
+// unrolled column loop stays small.
+#ifndef VBK_EMU
+__noinline__
+#endif
+__device__ double panel_rare_pivot(const DenseArgs& a, int b0, int nbb, int c, double mymax, double magc,
+                                   const double* blk, const double* sd, const double* sinv, const int* skeep,
+                                double* red, volatile int* s_cmd)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    if (lane == 0) *s_cmd = c;
+    __syncthreads();                                       // A: the helpers pick the command up
+    const double below = panel_colmax(a, b0, nbb, b0 + c, tid, nt, blk, sd, sinv, skeep);
+    red[tid] = fmax(mymax, below);
+    __syncthreads();                                       // B
+    double m = 0.0;
+    for (int u = lane; u < nt; u += 32) m = fmax(m, red[u]);
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, sft));
+    if (lane == 0) atomicAdd(&a.counters[C_NDEP], 1);
+    if (m < 1.0e+6 * 1.0e-8) return 0.0;
+    double sub = a.piv_scale * magc;
+    if (!(sub > 1.0e-8)) sub = 1.0e-8;
+    return (a.perm[a.T + a.p + b0 + c] < a.n_ld ? -1 : 1) * sub;
+}
+
 static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
 {
     VBK_DYN_SMEM(raw);
@@ -139,7 +210,9 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
     double* wm = sd + kPanelW;                                // [kPanelW] largest term magnitude of each diagonal entry
     double* sinv = wm + kPanelW;                              // [kPanelW] reciprocal pivots (0 for dropped rows)
     double* red = sinv + kPanelW;                             // [kDiagThreads]
-    int* skeep = reinterpret_cast<int*>(red + kDiagThreads);  // [kPanelW]
+    double* colbuf = red + kDiagThreads;                      // [3][64] column broadcast buffers of the warp LDL^T
+    int* skeep = reinterpret_cast<int*>(colbuf + 192);        // [kPanelW]
+    volatile int* s_cmd = skeep + kPanelW;                    // rare-path command slot (see below)
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p, nb = a.nb;
     long long tk = vbk_clock();
@@ -148,74 +221,122 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         for (int e = tid; e < kPanelW * kLDD; e += nt) blk[e] = 0.0;
     for (int e = tid; e < kPanelW; e += nt) { sd[e] = 1.0; sinv[e] = 0.0; skeep[e] = 0; wm[e] = (e < nb) ? a.wmag[p + e] : 0.0; }
     __syncthreads();
-#pragma unroll 8
+    // lower triangle of the block, column-major in HBM -> row-major (stride 129) in shared memory.  Asynchronous
+    // copies: 64 independent 8-byte transfers per thread in flight at once (plain load/store pairs were serialised
+    // by the compiler -- 18 us per panel, profiles/r01_summary.md)
     for (int e = tid; e < kPanelW * kPanelW; e += nt) {            // consecutive threads = consecutive rows: coalesced
         const int r = e % kPanelW, c = e / kPanelW;                // kPanelW is a power of two
-        if (r >= c && r < nb) blk[r * kLDD + c] = SW(a, p + r, p + c);
+        if (r >= c && r < nb) {
+#ifdef VBK_EMU
+            blk[r * kLDD + c] = SW(a, p + r, p + c);
+#else
+            cp_async8(&blk[r * kLDD + c], &SW(a, p + r, p + c), true);
+#endif
+        }
     }
+#ifndef VBK_EMU
+    cp_async_commit();
+    cp_async_wait<0>();
+#endif
     __syncthreads();
     panel_tick(a, 0, &tk);
 
     for (int b0 = 0; b0 < nb; b0 += 32) {
         const int nbb = (nb - b0 < 32) ? (nb - b0) : 32;
-        // ---- (a) the 32 x 32 sub-block, right-looking, by the whole CTA: per column one barrier, the pivot and
-        // its reciprocal (every thread for itself), then <= 4 independent updates per thread.  The columns keep
-        // a = l*d until the sub-block is finished (nobody reads a finished column again), so no thread ever
-        // waits for a scaled column: the dependent chain of a column is barrier + load + reciprocal + 2 multiplies
-        // (a warp-level left-looking version measured 1000+ cycles per column, profiles/).
-        for (int c = 0; c < nbb; ++c) {
-            __syncthreads();
-            double d = blk[(b0 + c) * kLDD + b0 + c];
-            const double magc = wm[b0 + c];
-            int keep = 1;
-            if (fabs(d) <= a.tol * magc) {                                     // uniform over the CTA; ldlt.c:600-614
-                double mymax = 0.0;
-                for (int r = c + 1 + tid; r < nbb; r += nt) mymax = fmax(mymax, fabs(blk[(b0 + r) * kLDD + b0 + c]));
-                const double below = panel_colmax(a, b0, nbb, b0 + c, tid, nt, blk, sd, sinv, skeep);
-                red[tid] = fmax(mymax, below);
-                __syncthreads();
-                double m = 0.0;
-                for (int u = 0; u < nt; ++u) m = fmax(m, red[u]);
-                __syncthreads();
-                if (m < 1.0e+6 * 1.0e-8) keep = 0;
-                else {
-                    double sub = a.piv_scale * magc;
-                    if (!(sub > 1.0e-8)) sub = 1.0e-8;
-                    d = (a.perm[a.T + p + b0 + c] < a.n_ld ? -1 : 1) * sub;
-                }
-                if (tid == 0) atomicAdd(&a.counters[C_NDEP], 1);
+        // ---- (a) the 32 x 32 sub-block: right-looking LDL^T by WARP 0 alone, row `lane` of the sub-block in the
+        // lane's registers.  Column c: the pivot comes by shuffle from lane c, every lane takes the reciprocal for
+        // itself, and the rank-1 update of the remaining columns is one shuffle (a_{j,c} from lane j) and one FMA
+        // per column and lane -- no barrier, no shared-memory round trip on the dependent chain (shuffle + reciprocal
+        // + multiply + FMA, ~110 cycles per column; the CTA-wide version with a barrier per column took 790,
+        // profiles/r01_summary.md).  A finished column is parked in shared memory as a = l*d (what the rare path
+        // and the scaling pass below expect).  The other warps wait in a command loop and only help in the rare
+        // dependent-pivot path (reference ldlt.c:600-614), which needs max |column| over all rows below.
+        if (warp == 0) {
+            // rows past a partial sub-block are padded with unit pivots (d = 1, nothing below them): the column
+            // loop below is then branch-free apart from the rare path, whatever nbb is
+            double ar[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                ar[j] = (lane < nbb && j <= lane) ? blk[(b0 + lane) * kLDD + b0 + j] : ((lane >= nbb && j == lane) ? 1.0 : 0.0);
+            double wmr = (lane < nbb) ? wm[b0 + lane] : 0.0;
+            if (ar[31] == 123.456) wmr += 1.0;                                 // (keeps the loads ahead of the tick)
+            panel_tick(a, 5, &tk);
+            // Column c of the current matrix is broadcast through a small shared-memory buffer (three copies in
+            // rotation, 16-byte aligned): one 8-byte store per lane, then every lane reads the pivot, and the
+            // a_{j,c} it needs two at a time.  (A shuffle per (c, j) pair made the unrolled loop 60 KB of code --
+            // twice the instruction cache -- and ran at 480 cycles per column; shuffles for the pivot alone were no
+            // faster than the shared-memory round trip, profiles/r01_summary.md.)
+            // The loop is software-pipelined by hand, because a warp issues in order: as soon as column c has
+            // updated a_{.,c+1} (ONE fma per lane), column c+1 is published and its pivot's reciprocal started; the
+            // other 30 - c updates of column c then fill that latency.  Dependent chain per column: fma, store,
+            // load, reciprocal (one MUFU + five fma, no slow-path call), multiply.
+            double d, magc, inv, nxt;
+            {
+                double* cb = colbuf;
+                cb[lane] = ar[0];
+                cb[32 + lane] = wmr;
+                __syncwarp();
+                d = cb[0]; magc = cb[32]; nxt = cb[1];
+                inv = vbk_rcp_fast(d);
             }
-            const double inv = keep ? vbk_rcp(d) : 0.0;
-            if (tid == 0) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
-            const int c2 = lane;
-            if (c2 > c && c2 < nbb) {
-                const double ac2 = blk[(b0 + c2) * kLDD + b0 + c] * inv;        // l_{c2,c}
-                // warp w owns rows w, w + nwarps, ...: all loads first, then the arithmetic, then the stores (a
-                // load-update-store loop is serialised by the compiler: the store may alias the next load)
-                constexpr int kRpw = 32 / (kDiagThreads / 32);
-                double ar[kRpw], tv[kRpw];
 #pragma unroll
-                for (int i = 0; i < kRpw; ++i) {
-                    const int r = warp + i * (kDiagThreads / 32);
-                    const bool on = r >= c2 && r < nbb;
-                    ar[i] = on ? blk[(b0 + r) * kLDD + b0 + c] : 0.0;           // a_{r,c}
-                    tv[i] = on ? blk[(b0 + r) * kLDD + b0 + c2] : 0.0;
+            for (int c = 0; c < 32; ++c) {
+                const double* cb = colbuf + (c % 3) * 64;
+                const double arc = ar[c];                                      // a_{r,c} = l_{r,c} d_c   (lanes r > c)
+                int keep = 1;
+                if (__builtin_expect(fabs(d) <= a.tol * magc, 0)) {            // uniform over the warp; ldlt.c:600-614
+                    const double nd = panel_rare_pivot(a, b0, nbb, c, (lane > c && lane < nbb) ? fabs(arc) : 0.0, magc,
+                                                       blk, sd, sinv, skeep, red, s_cmd);
+                    if (nd != 0.0) { d = nd; inv = vbk_rcp(d); }               // substituted pivot
+                    else { keep = 0; inv = 0.0; }                              // dependent row: dropped
                 }
+                const double lr = arc * inv;                                   // l_{r,c}
+                const bool mine = lane == c && c < nbb, below = lane > c && lane < nbb;
+                if (mine) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
+                if (below) blk[(b0 + lane) * kLDD + b0 + c] = arc;             // parked as l*d
+                const double term = fabs(lr * arc);                            // what this column adds to a_{r,r}
+                wmr = (below && term > wmr) ? term : wmr;
+                // a_{r,j} -= l_{r,c} d_c l_{j,c} = lr * a_{j,c}   (meaningful for r >= j; the rest is never read)
+                if (c + 1 < 32) {
+                    ar[c + 1] = fma(-lr, nxt, ar[c + 1]);                      // column c+1 is final now: publish it
+                    double* cn = colbuf + ((c + 1) % 3) * 64;
+                    cn[lane] = ar[c + 1];
+                    cn[32 + lane] = wmr;
+                    __syncwarp();
+                    d = cn[c + 1]; magc = cn[32 + c + 1]; nxt = (c + 2 < 32) ? cn[c + 2] : 0.0;
+                    inv = vbk_rcp_fast(d);
+                    // the rest of column c's update, in the shadow of that reciprocal
+                    if (c & 1) {                                               // c + 2 odd
+                        if (c + 2 < 32) ar[c + 2] = fma(-lr, cb[c + 2], ar[c + 2]);
 #pragma unroll
-                for (int i = 0; i < kRpw; ++i) {
-                    const int r = warp + i * (kDiagThreads / 32);
-                    const double upd = ar[i] * ac2;                             // a_{r,c} * l_{c2,c} = l d l
-                    tv[i] -= upd;
-                    if (r == c2 && fabs(upd) > wm[b0 + r]) wm[b0 + r] = fabs(upd);
-                }
+                        for (int j = c + 3; j < 32; j += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(cb + j);
+                            ar[j] = fma(-lr, v.x, ar[j]);
+                            ar[j + 1] = fma(-lr, v.y, ar[j + 1]);
+                        }
+                    } else {
 #pragma unroll
-                for (int i = 0; i < kRpw; ++i) {
-                    const int r = warp + i * (kDiagThreads / 32);
-                    if (r >= c2 && r < nbb) blk[(b0 + r) * kLDD + b0 + c2] = tv[i];
+                        for (int j = c + 2; j < 32; j += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(cb + j);
+                            ar[j] = fma(-lr, v.x, ar[j]);
+                            ar[j + 1] = fma(-lr, v.y, ar[j + 1]);
+                        }
+                    }
                 }
+            }
+            panel_tick(a, b0 == 0 ? 13 : 6, &tk);
+            if (lane < nbb) wm[b0 + lane] = wmr;
+            if (lane == 0) *s_cmd = -1;
+            __syncthreads();                                                   // A: releases the helpers
+        } else {
+            for (;;) {
+                __syncthreads();                                               // A
+                const int cmd = *s_cmd;
+                if (cmd < 0) break;
+                red[tid] = panel_colmax(a, b0, nbb, b0 + cmd, tid, nt, blk, sd, sinv, skeep);
+                __syncthreads();                                               // B
             }
         }
-        __syncthreads();
         // finished: a = l*d  ->  l   (dropped columns: inv = 0 gives l = 0)
         for (int e = tid; e < 32 * 32; e += nt) {
             const int r = e >> 5, c = e & 31;
@@ -232,17 +353,61 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
 #pragma unroll
             for (int c = 0; c < 32; ++c) l[c] = (c < nbb) ? blk[r * kLDD + b0 + c] : 0.0;
             trsm32(l, w, blk + b0 * kLDD + b0, kLDD, 1, sinv + b0, skeep + b0);
+            double dm = 0.0;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                if (c < nbb) { blk[r * kLDD + b0 + c] = l[c]; wbuf[t * 33 + c] = w[c]; }
+                if (c < nbb) { blk[r * kLDD + b0 + c] = l[c]; wbuf[t * 33 + c] = w[c]; dm = fmax(dm, fabs(l[c] * w[c])); }
             }
+            if (dm > wm[r]) wm[r] = dm;                                        // largest term of the update of a_{r,r} below
         }
         __syncthreads();
         panel_tick(a, 2, &tk);
         // ---- (c) rank-nbb update of the rest of the block (lower triangle incl. diagonal)
-        // 4 x 4 register tiles (16 FMAs per 8 shared-memory loads), rows and columns of a tile INTERLEAVED
-        // (tr + i*nt4, tc + j*nt4) so that consecutive threads touch consecutive rows: stride-129 / stride-33
-        // accesses are conflict-free, blocked tiles (stride 4*129) were 8-way conflicted
+#ifndef VBK_EMU
+        // 32 x 32 output blocks, one warp each, on the FP64 tensor path: 16 accumulator tiles, 8 steps of k.  Lane
+        // t of a fragment takes k = 16 (s / 4) + 4 t + s % 4 in step s (any assignment works as long as both
+        // operands use it): with the row strides 129 and 33 a half-warp then reads banks g + 4 t + const -- all
+        // different.  nbb == 32 here (a partial sub-block is the last one and has nothing below it).
+        {
+            const int g = lane >> 2, t4 = lane & 3;
+            const int nblk = (rem + 31) >> 5, npairs = nblk * (nblk + 1) / 2;
+            for (int pr = warp; pr < npairs; pr += (nt >> 5)) {
+                int bi = 0;
+                while ((bi + 1) * (bi + 2) / 2 <= pr) ++bi;
+                const int bj = pr - bi * (bi + 1) / 2;
+                double acc[4][4][2];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+                const double* Ap = blk + (b0 + nbb + 32 * bi + g) * kLDD + b0 + 4 * t4;
+                const double* Bp = wbuf + (32 * bj + g) * 33 + 4 * t4;
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) {
+                    const int kk = 16 * (s8 >> 2) + (s8 & 3);
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) av[mi] = Ap[mi * 8 * kLDD + kk];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) bv[ni] = (32 * bj + 8 * ni + g < rem) ? Bp[ni * 8 * 33 + kk] : 0.0;
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int rr = 32 * bi + 8 * mi + g, cc = 32 * bj + 8 * ni + 2 * t4 + j;
+                            if (rr < rem && cc <= rr) blk[(b0 + nbb + rr) * kLDD + b0 + nbb + cc] -= acc[mi][ni][j];
+                        }
+            }
+        }
+#else
+        // emulated build: 4 x 4 register tiles, rows and columns of a tile interleaved (tr + i*nt4, tc + j*nt4)
         {
             const int nt4 = (rem + 3) >> 2;
             for (int e = tid; e < nt4 * nt4; e += nt) {
@@ -252,7 +417,6 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-                double dmag[4] = {0.0, 0.0, 0.0, 0.0};
                 for (int c = 0; c < nbb; ++c) {
                     double lv[4], wv[4];
 #pragma unroll
@@ -264,10 +428,6 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[i][j] = fma(lv[i], wv[j], acc[i][j]);
-                    if (tr == tc) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) dmag[i] = fmax(dmag[i], fabs(lv[i] * wv[i]));
-                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -276,15 +436,9 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
                         const int rr = tr + i * nt4, cc = tc + j * nt4;
                         if (rr < rem && cc < rem && rr >= cc) blk[(b0 + nbb + rr) * kLDD + b0 + nbb + cc] -= acc[i][j];
                     }
-                if (tr == tc) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = tr + i * nt4;
-                        if (rr < rem && dmag[i] > wm[b0 + nbb + rr]) wm[b0 + nbb + rr] = dmag[i];
-                    }
-                }
             }
         }
+#endif
         __syncthreads();
         panel_tick(a, 3, &tk);
     }

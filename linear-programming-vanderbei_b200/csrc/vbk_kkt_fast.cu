@@ -1,6 +1,6 @@
 // vbk_kkt_fast.cu -- host orchestration of FAST mode (kernels in vbk_fast.cuh).
 #include "vbk_kkt.h"
-#include "vbk_fast3.cuh"
+#include "vbk_fast4.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -39,6 +39,9 @@ void Kkt::prepare_fast()
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdPipeSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128>::kSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsSmem));
 #endif
@@ -130,6 +133,21 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         // a few SMs.  Hazards: B_k reads P_k and the columns of panel k and writes strictly-lower entries right of
         // panel k+1 only -- nothing panel k+1's kernels touch (they write their own columns, the other P buffer and
         // diagonal entries); A_{k+1} and rows_{k+2} (which reuses P_k's buffer) wait for B_k.
+        // rank-128 trailing update (vbk_fast4.cuh): DMMA tiles fed by a cp.async ring; $VBK_UPDATE=m128 / p select 128 x 128 DMMA tiles / the
+        // DFMA version of the same pipeline, $VBK_UPDATE=k the unpipelined second-generation kernel (A/B runs)
+#ifdef VBK_EMU
+        auto launch_update = [&](int tiles, cudaStream_t st, const DenseArgs& d) {
+            VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, st, d);
+        };
+#else
+        const std::string upd = eu ? eu : "";
+        auto launch_update = [&](int tiles, cudaStream_t st, const DenseArgs& d) {
+            if (upd == "k") VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, st, d);
+            else if (upd == "p") VBK_LAUNCH(k_dense_update_p, dim3(tiles, tiles), 256, kUpdPipeSmem, st, d);
+            else if (upd == "m128") VBK_LAUNCH(k_dense_update_m<128>, dim3(tiles, tiles), UpdMma<128>::kThreads, UpdMma<128>::kSmem, st, d);
+            else VBK_LAUNCH(k_dense_update_m<64>, dim3(2 * tiles, tiles), UpdMma<64>::kThreads, UpdMma<64>::kSmem, st, d);
+        };
+#endif
         int k = 0, last_b = -1;
         for (int P0 = 0; P0 < W; P0 += kPanelW, ++k) {
             da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0;
@@ -146,7 +164,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             if (!lookahead) {
                 da.rbase = kend; da.cmax = W;
                 const int tiles = (below + kUpdTD - 1) / kUpdTD;
-                VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
+                launch_update(tiles, stream_, da);
                 ++launches;
                 continue;
             }
@@ -159,7 +177,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
                 DenseArgs db = da;
                 db.rbase = kend + kPanelW; db.cmax = W;
                 const int tiles = (rest + kUpdTD - 1) / kUpdTD;
-                VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, sB, db);
+                launch_update(tiles, sB, db);
 #ifndef VBK_EMU
                 VBK_CUDA(cudaEventRecord(ev_updb_[k & 1], sB));
 #endif
@@ -184,8 +202,8 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         panel_prof_.download(h, 16, stream_);
         VBK_CUDA(cudaStreamSynchronize(stream_));
         std::fprintf(stderr, "vbkkt panel profile (cycles of thread 0, CTA 0, summed over %d panels): diag load %llu, warp LDL %llu, "
-                     "block trsm %llu, block update %llu, store %llu | rows: panel fetch %llu, row loads %llu, rank update %llu, "
-                     "stages %llu, stores %llu\n", (W + kPanelW - 1) / kPanelW, h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
+                     "(registers %llu, columns of the first sub-block %llu, of the others %llu) block trsm %llu, block update %llu, store %llu | rows: panel fetch %llu, row loads %llu, rank update %llu, "
+                     "stages %llu, stores %llu\n", (W + kPanelW - 1) / kPanelW, h[0], h[1] + h[5] + h[6] + h[13], h[5], h[13], h[6], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
     }
     if (dense_v2) {
         // two-level blocking (vbk_fast2.cuh): inner panels of panel_nb_ columns, one rank-(outer) update of
