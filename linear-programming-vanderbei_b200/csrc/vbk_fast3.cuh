@@ -284,7 +284,11 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
                 const double* cb = colbuf + (c % 3) * 64;
                 const double arc = ar[c];                                      // a_{r,c} = l_{r,c} d_c   (lanes r > c)
                 int keep = 1;
+#ifdef VBK_X1
+                if (false) {
+#else
                 if (__builtin_expect(fabs(d) <= a.tol * magc, 0)) {            // uniform over the warp; ldlt.c:600-614
+#endif
                     const double nd = panel_rare_pivot(a, b0, nbb, c, (lane > c && lane < nbb) ? fabs(arc) : 0.0, magc,
                                                        blk, sd, sinv, skeep, red, s_cmd);
                     if (nd != 0.0) { d = nd; inv = vbk_rcp(d); }               // substituted pivot
@@ -292,10 +296,14 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
                 }
                 const double lr = arc * inv;                                   // l_{r,c}
                 const bool mine = lane == c && c < nbb, below = lane > c && lane < nbb;
+#ifndef VBK_X2
                 if (mine) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
                 if (below) blk[(b0 + lane) * kLDD + b0 + c] = arc;             // parked as l*d
                 const double term = fabs(lr * arc);                            // what this column adds to a_{r,r}
                 wmr = (below && term > wmr) ? term : wmr;
+#else
+                if (mine) { sinv[b0 + c] = inv; }
+#endif
                 // a_{r,j} -= l_{r,c} d_c l_{j,c} = lr * a_{j,c}   (meaningful for r >= j; the rest is never read)
                 if (c + 1 < 32) {
                     ar[c + 1] = fma(-lr, nxt, ar[c + 1]);                      // column c+1 is final now: publish it

@@ -144,7 +144,11 @@ private:
     bool fast_ready_ = false, light_schur_ = false;
     int panel_nb_ = 32;
     DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_, panel_buf_;
-    DevArray<int> wmark_, pan_keep_, tri_flags_;
+    DevArray<int> wmark_, pan_keep_, tri_flags_, tri3_flags_;
+    DevArray<int> sp_end_, sp_lvlcol_;          // fast sparse columns (vbk_fast6.cuh): sparse prefix ends, columns by level
+    std::vector<int> sp_lvlptr_;
+    int sp_cap_ = 2, sp_cap_heavy_ = 2;
+    DevArray<double> tinv_, tri_racc_;          // inverted diagonal blocks + slice accumulators of the 128-row sweeps (vbk_fast5.cuh)
     DevArray<unsigned long long> panel_prof_;
     // look-ahead: the bulk of a panel's trailing update runs on a second stream while the next panel is factorised
     cudaStream_t stream2_ = 0;

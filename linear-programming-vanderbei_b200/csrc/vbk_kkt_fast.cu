@@ -1,6 +1,6 @@
 // vbk_kkt_fast.cu -- host orchestration of FAST mode (kernels in vbk_fast.cuh).
 #include "vbk_kkt.h"
-#include "vbk_fast4.cuh"
+#include "vbk_fast6.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -21,14 +21,53 @@ void Kkt::prepare_fast()
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
     pan_d_.alloc(kPanelW); pan_keep_.alloc(kPanelW); panel_buf_.alloc(kPanelBufDoubles);
     tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
+#ifndef VBK_EMU
+    {
+        const int npan = (W + kTriPW - 1) / kTriPW;
+        tinv_.alloc((size_t)npan * kTriPW * kTriPW);
+        tri_racc_.alloc((size_t)npan * kTriPW);
+        tri3_flags_.alloc((size_t)2 * npan + 1);
+    }
+#endif
     {
         // how many sparse-column contributions do the window rows see?  Few => light Schur kernel.
         long long nsc = 0;
+        std::vector<int> spend((size_t)W);
         for (int i = T; i < N; ++i) {
             const int* b = sym_.rj_asc.data() + sym_.rowptr[i];
             const int* e = sym_.rj_asc.data() + sym_.rowptr[i + 1];
-            nsc += std::lower_bound(b, e, T) - b;
+            const long long cnt = std::lower_bound(b, e, T) - b;
+            nsc += cnt;
+            spend[(size_t)(i - T)] = sym_.rowptr[i] + (int)cnt;
         }
+        sp_end_.upload(spend, stream_);
+        // etree levels of the sparse columns (parent restricted to j < T): every level is one launch of
+        // k_sparse_level for its light columns and one of k_sparse_level_heavy for the heavy ones (vbk_fast6.cuh).
+        // weight of a column = entries its contributors' tails apply to it
+        std::vector<int> lev((size_t)std::max(T, 1), 0);
+        std::vector<char> heavy((size_t)std::max(T, 1), 0);
+        int nlev = 0, cap_l = 1, cap_h = 1;
+        const long long heavy_w = std::getenv("VBK_SPARSE_HEAVY") ? std::atoll(std::getenv("VBK_SPARSE_HEAVY")) : 2048;
+        for (int j = 0; j < T; ++j) {
+            const int pj = sym_.parent[j];
+            if (pj >= 0 && pj < T && lev[pj] < lev[j] + 1) lev[pj] = lev[j] + 1;
+            nlev = std::max(nlev, lev[j] + 1);
+            long long wgt = 0;
+            for (int t = sym_.rowptr[j]; t < sym_.rowptr[j + 1]; ++t)
+                wgt += sym_.kL[sym_.rj_asc[t] + 1] - sym_.rk_asc[t] - 1;
+            heavy[j] = wgt > heavy_w;
+            int& cap = heavy[j] ? cap_h : cap_l;
+            cap = std::max(cap, sym_.kL[j + 1] - sym_.kL[j]);
+        }
+        // per level: light columns first, then heavy ones; sp_lvlptr_ has 2 entries per level + end
+        sp_lvlptr_.assign((size_t)2 * nlev + 1, 0);
+        for (int j = 0; j < T; ++j) ++sp_lvlptr_[(size_t)2 * lev[j] + (heavy[j] ? 1 : 0) + 1];
+        for (size_t l = 0; l + 1 < sp_lvlptr_.size(); ++l) sp_lvlptr_[l + 1] += sp_lvlptr_[l];
+        std::vector<int> cols((size_t)std::max(T, 1)), fill(sp_lvlptr_.begin(), sp_lvlptr_.end());
+        for (int j = 0; j < T; ++j) cols[(size_t)fill[(size_t)2 * lev[j] + (heavy[j] ? 1 : 0)]++] = j;
+        sp_lvlcol_.upload(cols, stream_);
+        sp_cap_ = (cap_l + 1) & ~1;
+        sp_cap_heavy_ = (cap_h + 1) & ~1;
         const char* es = std::getenv("VBK_SCHUR");
         light_schur_ = es ? (std::string(es) == "light") : (nsc <= 128LL * W);
     }
@@ -42,6 +81,11 @@ void Kkt::prepare_fast()
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdPipeSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64>::kSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_sparse_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_sparse_level_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_schur_window2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_window_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTinvSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_window_tri3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriV3Smem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsSmem));
 #endif
@@ -65,13 +109,57 @@ void Kkt::factor_window_fast(TiledArgs& ta)
 
     // 1. columns j < T: the strict task kernel (bit-exact for these columns, dependent-pivot rule
     //    included).  k_tiled_reset has already run.
-    if (sparse_tasks > 0) {
+    int launches = 2;
+#ifndef VBK_EMU
+    // throughput kernels of vbk_fast6.cuh unless $VBK_SPARSE=strict / $VBK_SCHUR=light|heavy ask for the first generation
+    const char* esp = std::getenv("VBK_SPARSE");
+    const size_t sp_smem = (size_t)kSpWarps * sp_cap_ * (2 * sizeof(double) + sizeof(int));
+    const size_t sph_smem = sizeof(double) * ((size_t)2 * sp_cap_heavy_ + 2 * kSpHeavyBatch + kSpHeavyThreads)
+                            + sizeof(int) * ((size_t)sp_cap_heavy_ + W + 2 * kSpHeavyBatch + 2);
+    const bool sparse_levels = !(esp && std::string(esp) == "strict") && sp_smem <= (size_t)smem_optin_ && sph_smem <= (size_t)smem_optin_;
+#else
+    const bool sparse_levels = false;
+#endif
+    if (sparse_tasks > 0 && !sparse_levels) {
         ta.phase = 0; ta.task_base = 0; ta.ntasks = sparse_tasks;
         VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(sparse_tasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
     }
+#ifndef VBK_EMU
+    if (T > 0 && sparse_levels) {
+        SparseLevelArgs sl;
+        sl.n_ld = sym_.n; sl.T = T; sl.W = W; sl.kL = kL_.p; sl.iL = iL_.p; sl.L = L_.p; sl.diag = diag_.p; sl.mark = mark_.p;
+        sl.perm = perm_.p; sl.rowptr = rowptr_.p; sl.rk = rk_sig_.p; sl.rj = rj_sig_.p; sl.counters = counters_.p;
+        sl.scal_bits = bits_.p; sl.epsnum = ta.epsnum;
+        for (size_t l = 0; l + 2 < sp_lvlptr_.size(); l += 2) {
+            const int nl = sp_lvlptr_[l + 1] - sp_lvlptr_[l], nh = sp_lvlptr_[l + 2] - sp_lvlptr_[l + 1];
+            if (nl > 0) {
+                sl.cols = sp_lvlcol_.p + sp_lvlptr_[l]; sl.ncols = nl; sl.cap = sp_cap_;
+                const int g = std::max(1, std::min((nl + kSpWarps - 1) / kSpWarps, num_sms_ * 8));
+                VBK_LAUNCH(k_sparse_level, g, kSpWarps * 32, sp_smem, stream_, sl);
+                ++launches;
+            }
+            if (nh > 0) {
+                sl.cols = sp_lvlcol_.p + sp_lvlptr_[l + 1]; sl.ncols = nh; sl.cap = sp_cap_heavy_;
+                VBK_LAUNCH(k_sparse_level_heavy, std::min(nh, num_sms_ * 2), kSpHeavyThreads, sph_smem, stream_, sl);
+                ++launches;
+            }
+        }
+    }
+#endif
     // 2. Schur complement of the sparse columns on the window, written densely; no dependencies.
     //    Entries outside the fill pattern are never written: start from zero.
     VBK_CUDA(cudaMemsetAsync(Sw_.p, 0, sizeof(double) * (size_t)W * W, stream_));
+#ifndef VBK_EMU
+    const char* esc = std::getenv("VBK_SCHUR");
+    const size_t sc2_smem = sizeof(double) * ((size_t)W + 2 * kSchur2Batch) + sizeof(int) * 2 * kSchur2Batch;
+    const bool schur2 = !esc && sc2_smem <= (size_t)smem_optin_;
+    if (schur2) {
+        Schur2Args sc;
+        sc.N = N; sc.T = T; sc.ld = W; sc.cap = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
+        sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.spend = sp_end_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;
+        VBK_LAUNCH(k_schur_window2, std::min(W, num_sms_ * 4), kSchur2Threads, sc2_smem, stream_, sc);
+    } else
+#endif
     if (light_schur_) {
         SchurArgs sc;
         sc.N = N; sc.T = T; sc.ld = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
@@ -107,7 +195,6 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     const size_t sm_upd_rt = sizeof(double) * 2 * kPanelMax * kUpdTD;
     const char* eu = std::getenv("VBK_UPDATE");
     const bool simple_update = eu && std::string(eu) == "simple";
-    int launches = 2;
     const char* ed = std::getenv("VBK_DENSE");
     const bool dense_v1 = ed && std::string(ed) == "v1";
     const bool dense_v2 = ed && std::string(ed) == "v2";
@@ -261,6 +348,11 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         VBK_LAUNCH(k_window_mirror, dim3(nt32, nt32), kVecThreads, 32 * 33 * sizeof(double), stream_, W, W, Sw_.p);
         ++launches;
     }
+#ifndef VBK_EMU
+    // 4b. inverses of the 128 x 128 diagonal blocks for the triangular sweeps (vbk_fast5.cuh)
+    VBK_LAUNCH(k_window_tinv, (W + kTriPW - 1) / kTriPW, kTriPW, kTinvSmem, stream_, W, W, Sw_.p, tinv_.p);
+    ++launches;
+#endif
     // 5. back into the packed storage the strict-layout consumers (tests, get_factor) read
     {
         const int gx = std::max(1, std::min((W + kVecThreads - 1) / kVecThreads, 64));
@@ -295,7 +387,25 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     tr.flags = tri_flags_.p; tr.counters = counters_.p; tr.scal_bits = bits_.p; tr.epssol = 1.0e-6;
     const int gtri = std::max(1, std::min(tr.npanels, num_sms_));
     const size_t sm_tri = (size_t)(kTriThreads / 32) * 32 * sizeof(double) + 16;   // + the claim slot
+#ifndef VBK_EMU
+    const bool wsolve_v2 = ew && std::string(ew) == "v2";
+    Tri3Args t3;
+    t3.W = W; t3.ld = W; t3.npan = (W + kTriPW - 1) / kTriPW; t3.S = Sw_.p; t3.Tinv = tinv_.p; t3.z = z_.p + T;
+    t3.mark = mark_.p + T; t3.racc = tri_racc_.p; t3.flags = tri3_flags_.p; t3.counters = counters_.p;
+    t3.scal_bits = bits_.p; t3.epssol = 1.0e-6;
+    const int g3 = std::max(1, std::min(t3.npan * kTriSplit, num_sms_));
+    auto sweep3 = [&](int dir) {
+        VBK_CUDA(cudaMemsetAsync(tri3_flags_.p, 0, sizeof(int) * (size_t)(2 * t3.npan + 1), stream_));
+        VBK_CUDA(cudaMemsetAsync(tri_racc_.p, 0, sizeof(double) * (size_t)t3.npan * kTriPW, stream_));
+        t3.dir = dir;
+        VBK_LAUNCH(k_window_tri3, g3, kTriV3Threads, kTriV3Smem, stream_, t3);
+    };
+#else
+    const bool wsolve_v2 = true;
+    auto sweep3 = [&](int) {};
+#endif
     if (wsolve_v1) VBK_LAUNCH(k_window_fwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    else if (!wsolve_v2) sweep3(0);
     else {
         VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)(tr.npanels + 1), stream_));
         tr.dir = 0;
@@ -303,6 +413,7 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     }
     VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
     if (wsolve_v1) VBK_LAUNCH(k_window_bwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
+    else if (!wsolve_v2) sweep3(1);
     else {
         VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)(tr.npanels + 1), stream_));
         tr.dir = 1;
