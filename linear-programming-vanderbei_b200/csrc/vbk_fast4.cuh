@@ -187,7 +187,7 @@ static __global__ void __launch_bounds__(UpdMma<TN>::kThreads, 256 / UpdMma<TN>:
     if (r0 + kUpT <= c0 || c0 >= a.cmax) return;             // tile entirely above the diagonal / outside
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;   // this warp's 64 x 32 corner of the tile
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;   // this warp's corner: 64 rows x 32 columns of S
     const double* Ag = a.S + (size_t)a.kcol0 * a.ld;
     const double* Bg = a.P + (size_t)a.pcol0 * a.W;
     const bool al16 = ((a.ld | a.W | r0 | c0) & 1) == 0 && ((((size_t)a.S) | ((size_t)a.P)) & 15) == 0;
@@ -195,25 +195,40 @@ static __global__ void __launch_bounds__(UpdMma<TN>::kThreads, 256 / UpdMma<TN>:
     // a warp tile that lies entirely on or above the diagonal has nothing to compute
     const bool dead = r0 + wm + 63 <= c0 + wn;
 
+    // Copy addressing, hoisted (the per-slab address arithmetic was 16 % of the kernel's issue slots, ncu source
+    // page of round 1): with 16-byte copies a thread always moves the same pair of rows, slab row c = ca + i * cstep.
+    constexpr int kRowsA = 2 * U::kThreads / kUpT, kRowsB = 2 * U::kThreads / TN;   // slab rows covered per pass
+    const int xa = (tid % (kUpT / 2)) * 2, ca = tid / (kUpT / 2);
+    const int xb = (tid % (TN / 2)) * 2, cbr = tid / (TN / 2);
+    const bool aok = r0 + xa < a.W, bok = c0 + xb < a.W;
+    const double* pa = aok ? Ag + (size_t)(r0 + xa) + (size_t)ca * a.ld : Ag;
+    const double* pb = bok ? Bg + (size_t)(c0 + xb) + (size_t)cbr * a.W : Bg;
+    const unsigned sa0 = (unsigned)__cvta_generic_to_shared(sm + ca * kMmLd + xa);
+    const unsigned sb0 = (unsigned)__cvta_generic_to_shared(sm + kUpKC * kMmLd + cbr * U::kLdB + xb);
+    const size_t astep = (size_t)kRowsA * a.ld, bstep = (size_t)kRowsB * a.W;
+
     auto issue = [&](int s) {
         if (s < nslab) {
-            double* As = sm + (size_t)(s % kUpStages) * U::kStage;
-            double* Bs = As + kUpKC * kMmLd;
             const int kc = s * kUpKC;
             if (al16) {
+                const unsigned so = (unsigned)((s % kUpStages) * U::kStage * sizeof(double));
+                const double* qa = pa + (size_t)kc * a.ld;
+                const double* qb = pb + (size_t)kc * a.W;
 #pragma unroll
-                for (int i = 0; i < kUpKC * kUpT / 2 / U::kThreads; ++i) {
-                    const int e = tid + i * U::kThreads, x = (e % (kUpT / 2)) * 2, c = e / (kUpT / 2);
-                    const bool ok = kc + c < a.klen && r0 + x < a.W;
-                    cp_async16(As + c * kMmLd + x, ok ? Ag + (size_t)(r0 + x) + (size_t)(kc + c) * a.ld : Ag, ok);
+                for (int i = 0; i < kUpKC / kRowsA; ++i) {
+                    const int n = (aok && kc + ca + i * kRowsA < a.klen) ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+                                 ::"r"(sa0 + so + (unsigned)(i * kRowsA * kMmLd * sizeof(double))), "l"(n ? qa + i * astep : Ag), "r"(n) : "memory");
                 }
 #pragma unroll
-                for (int i = 0; i < kUpKC * TN / 2 / U::kThreads; ++i) {
-                    const int e = tid + i * U::kThreads, x = (e % (TN / 2)) * 2, c = e / (TN / 2);
-                    const bool ok = kc + c < a.klen && c0 + x < a.W;
-                    cp_async16(Bs + c * U::kLdB + x, ok ? Bg + (size_t)(c0 + x) + (size_t)(kc + c) * a.W : Bg, ok);
+                for (int i = 0; i < kUpKC / kRowsB; ++i) {
+                    const int n = (bok && kc + cbr + i * kRowsB < a.klen) ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+                                 ::"r"(sb0 + so + (unsigned)(i * kRowsB * U::kLdB * sizeof(double))), "l"(n ? qb + i * bstep : Bg), "r"(n) : "memory");
                 }
             } else {
+                double* As = sm + (size_t)(s % kUpStages) * U::kStage;
+                double* Bs = As + kUpKC * kMmLd;
 #pragma unroll
                 for (int i = 0; i < kUpKC * kUpT / U::kThreads; ++i) {
                     const int e = tid + i * U::kThreads, x = e % kUpT, c = e / kUpT;
@@ -231,11 +246,14 @@ static __global__ void __launch_bounds__(UpdMma<TN>::kThreads, 256 / UpdMma<TN>:
         cp_async_commit();
     };
 
-    double acc[8][4][2];
+    // The MMA's M index runs over COLUMNS of S (operand "A" = rows of P), its N index over ROWS of S (operand "B" =
+    // rows of L21): a thread then holds C[g][2t], C[g][2t+1] = two consecutive rows of one column of S, and the
+    // read-modify-write of the tile is 16 bytes wide.
+    double acc[4][8][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+        for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
 
     issue(0);
     issue(1);
@@ -244,49 +262,63 @@ static __global__ void __launch_bounds__(UpdMma<TN>::kThreads, 256 / UpdMma<TN>:
         __syncthreads();
         issue(s + 2);
         if (dead) continue;
-        const double* As = sm + (size_t)(s % kUpStages) * U::kStage + wm + g;
-        const double* Bs = sm + (size_t)(s % kUpStages) * U::kStage + kUpKC * kMmLd + wn + g;
+        const double* As = sm + (size_t)(s % kUpStages) * U::kStage + wm + g;                       // rows of S
+        const double* Bs = sm + (size_t)(s % kUpStages) * U::kStage + kUpKC * kMmLd + wn + g;       // columns of S
 #pragma unroll
         for (int k4 = 0; k4 < kUpKC / 4; ++k4) {
-            double av[8], bv[4];
+            double cv[4], rv[8];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) av[mi] = As[(k4 * 4 + t) * kMmLd + mi * 8];
+            for (int mi = 0; mi < 4; ++mi) cv[mi] = Bs[(k4 * 4 + t) * U::kLdB + mi * 8];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) bv[ni] = Bs[(k4 * 4 + t) * U::kLdB + ni * 8];
+            for (int ni = 0; ni < 8; ++ni) rv[ni] = As[(k4 * 4 + t) * kMmLd + ni * 8];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
+            for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+                for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], cv[mi], rv[ni]);
         }
     }
     cp_async_wait<0>();
     if (dead) return;
 
-    // epilogue: loads of one 8-column block (16 values per thread) first, then subtract, then store
-    const int rb = r0 + wm + g, cb = c0 + wn + 2 * t;
+    // epilogue, one 8-column block at a time: 8 independent loads, subtract, store (a load-subtract-store per element
+    // is serialised by the compiler -- a store may alias the next load)
+    const int rb = r0 + wm + 2 * t, cb = c0 + wn + g;
     const bool interior = r0 >= c0 + TN && r0 + kUpT <= a.W && c0 + TN <= a.cmax;
+    if (interior && al16) {
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
+        for (int mi = 0; mi < 4; ++mi) {
+            double2 tv[8];
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) tv[ni] = *reinterpret_cast<const double2*>(&SW(a, rb + ni * 8, cb + mi * 8));
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) { tv[ni].x -= acc[mi][ni][0]; tv[ni].y -= acc[mi][ni][1]; }
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) *reinterpret_cast<double2*>(&SW(a, rb + ni * 8, cb + mi * 8)) = tv[ni];
+        }
+        return;
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
         double tv[8][2];
+        const int c = cb + mi * 8;
+        const bool cok = c < a.W && c < a.cmax;
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int r = rb + mi * 8, c = cb + ni * 8 + j;
-                const bool ok = interior || (r < a.W && c < a.W && c < a.cmax && r > c);
-                tv[mi][j] = ok ? SW(a, r, c) : 0.0;
+                const int r = rb + ni * 8 + j;
+                tv[ni][j] = (cok && r < a.W && r > c) ? SW(a, r, c) : 0.0;
             }
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tv[mi][j] -= acc[mi][ni][j];
+            for (int j = 0; j < 2; ++j) tv[ni][j] -= acc[mi][ni][j];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int r = rb + mi * 8, c = cb + ni * 8 + j;
-                const bool ok = interior || (r < a.W && c < a.W && c < a.cmax && r > c);
-                if (ok) SW(a, r, c) = tv[mi][j];
+                const int r = rb + ni * 8 + j;
+                if (cok && r < a.W && r > c) SW(a, r, c) = tv[ni][j];
             }
     }
 }

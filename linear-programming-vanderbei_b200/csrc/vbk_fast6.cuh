@@ -177,30 +177,41 @@ static __global__ void __launch_bounds__(kSpHeavyThreads) k_sparse_level_heavy(S
             for (int b = 0; b < nb; ++b) d = d - sp[b];                    // every thread keeps its own copy of diagi
             // software pipeline over the contributors, four at a time: the tid-th tail entries of the NEXT four are in
             // flight while these four are applied (one L2 round trip per four contributors instead of per contributor)
-            int rq[4]; double vq[4];
+            int rq[4][2]; double vq[4][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                rq[u] = -1; vq[u] = 0.0;
-                if (u < nb) { const int e = se0[u] + tid; if (e < se1[u]) { rq[u] = a.iL[e]; vq[u] = a.L[e]; } }
-            }
-            for (int b = 0; b < nb; b += 4) {
-                int rc[4]; double vc[4];
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { rc[u] = rq[u]; vc[u] = vq[u]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    rq[u] = -1;
-                    if (b + 4 + u < nb) { const int e = se0[b + 4 + u] + tid; if (e < se1[b + 4 + u]) { rq[u] = a.iL[e]; vq[u] = a.L[e]; } }
+                for (int h = 0; h < 2; ++h) {
+                    rq[u][h] = -1; vq[u][h] = 0.0;
+                    if (u < nb) { const int e = se0[u] + tid + h * kSpHeavyThreads; if (e < se1[u]) { rq[u][h] = a.iL[e]; vq[u][h] = a.L[e]; } }
                 }
+            for (int b = 0; b < nb; b += 4) {
+                int rc[4][2]; double vc[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { rc[u][h] = rq[u][h]; vc[u][h] = vq[u][h]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        rq[u][h] = -1;
+                        if (b + 4 + u < nb) {
+                            const int e = se0[b + 4 + u] + tid + h * kSpHeavyThreads;
+                            if (e < se1[b + 4 + u]) { rq[u][h] = a.iL[e]; vq[u][h] = a.L[e]; }
+                        }
+                    }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (b + u >= nb) break;                                   // uniform
                     const double wb = sw[b + u];
-                    if (rc[u] >= 0) {
-                        const int slot = (rc[u] >= a.T) ? winmap[rc[u] - a.T] : sp_find(rows, ncs, rc[u]);
-                        acc[slot] = acc[slot] + wb * vc[u];
-                    }
-                    for (int e = se0[b + u] + kSpHeavyThreads + tid; e < se1[b + u]; e += kSpHeavyThreads) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (rc[u][h] >= 0) {
+                            const int slot = (rc[u][h] >= a.T) ? winmap[rc[u][h] - a.T] : sp_find(rows, ncs, rc[u][h]);
+                            acc[slot] = acc[slot] + wb * vc[u][h];
+                        }
+                    for (int e = se0[b + u] + 2 * kSpHeavyThreads + tid; e < se1[b + u]; e += kSpHeavyThreads) {
                         const int r = a.iL[e];
                         const int slot = (r >= a.T) ? winmap[r - a.T] : sp_find(rows, ncs, r);
                         acc[slot] = acc[slot] + wb * a.L[e];
@@ -267,27 +278,38 @@ static __global__ void __launch_bounds__(kSchur2Threads) k_schur_window2(Schur2A
             const int nb = (tend - tb < kSchur2Batch) ? (tend - tb) : kSchur2Batch;
             // contributors one after the other (two of them may meet in a row; a fixed order also keeps the result
             // the same from run to run), every thread on one tail; the next four tails' entries are in flight meanwhile
-            int rq[4]; double vq[4];
+            int rq[4][2]; double vq[4][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                rq[u] = -1; vq[u] = 0.0;
-                if (u < nb) { const int e = se0[u] + tid; if (e < se1[u]) { rq[u] = a.iL[e]; vq[u] = a.L[e]; } }
-            }
-            for (int b = 0; b < nb; b += 4) {
-                int rc[4]; double vc[4];
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { rc[u] = rq[u]; vc[u] = vq[u]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    rq[u] = -1;
-                    if (b + 4 + u < nb) { const int e = se0[b + 4 + u] + tid; if (e < se1[b + 4 + u]) { rq[u] = a.iL[e]; vq[u] = a.L[e]; } }
+                for (int h = 0; h < 2; ++h) {
+                    rq[u][h] = -1; vq[u][h] = 0.0;
+                    if (u < nb) { const int e = se0[u] + tid + h * kSchur2Threads; if (e < se1[u]) { rq[u][h] = a.iL[e]; vq[u][h] = a.L[e]; } }
                 }
+            for (int b = 0; b < nb; b += 4) {
+                int rc[4][2]; double vc[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { rc[u][h] = rq[u][h]; vc[u][h] = vq[u][h]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        rq[u][h] = -1;
+                        if (b + 4 + u < nb) {
+                            const int e = se0[b + 4 + u] + tid + h * kSchur2Threads;
+                            if (e < se1[b + 4 + u]) { rq[u][h] = a.iL[e]; vq[u][h] = a.L[e]; }
+                        }
+                    }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (b + u >= nb) break;                                   // uniform
                     const double wb = -sw[b + u];
-                    if (rc[u] >= 0) acc[rc[u] - i] = fma(wb, vc[u], acc[rc[u] - i]);
-                    for (int e = se0[b + u] + kSchur2Threads + tid; e < se1[b + u]; e += kSchur2Threads)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (rc[u][h] >= 0) acc[rc[u][h] - i] = fma(wb, vc[u][h], acc[rc[u][h] - i]);
+                    for (int e = se0[b + u] + 2 * kSchur2Threads + tid; e < se1[b + u]; e += kSchur2Threads)
                         acc[a.iL[e] - i] = fma(wb, a.L[e], acc[a.iL[e] - i]);
                     __syncthreads();
                 }

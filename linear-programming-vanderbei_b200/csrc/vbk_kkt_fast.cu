@@ -157,7 +157,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         Schur2Args sc;
         sc.N = N; sc.T = T; sc.ld = W; sc.cap = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
         sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.spend = sp_end_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;
-        VBK_LAUNCH(k_schur_window2, std::min(W, num_sms_ * 4), kSchur2Threads, sc2_smem, stream_, sc);
+        VBK_LAUNCH(k_schur_window2, std::min(W, num_sms_ * 6), kSchur2Threads, sc2_smem, stream_, sc);
     } else
 #endif
     if (light_schur_) {

@@ -117,6 +117,64 @@ def test_fast_mode_big_iterates_match_reference_solution(vbkkt, gpu_lib):
         K.close()
 
 
+@pytest.mark.parametrize("name,it", [("afiro", 26), ("25fv47", 20), ("pds-02", 20), ("dfl001", 20)])
+def test_fast_mode_sparse_columns_bit_exact(vbkkt, gpu_lib, oracle_lib, name, it):
+    """Fast mode keeps the reference's arithmetic for the sparse columns j < T (level-scheduled kernels of
+    vbk_fast6.cuh: contributors in the reference's list order, separately rounded products and sums, exact pivot
+    rule): their part of L, diag and mark equals the strict factor -- itself bit-equal to the reference -- bit for
+    bit, dependent pivots included (afiro iterate 26 has two)."""
+    lp = H.load_fixture(name)
+    if name in ("afiro", "25fv47"):
+        E, D, *_ = H.capture_step(oracle_lib, lp, "hsd", it)
+    else:
+        z = np.load(H.GOLDEN / "iterates" / f"{name}_it{it}.npz") if name == "dfl001" else None
+        E, D = (z["E"], z["D"]) if z is not None else (np.random.default_rng(3).uniform(0.1, 10.0, lp.m),
+                                                      np.random.default_rng(4).uniform(0.1, 10.0, lp.n))
+    Ks = H.kkt_for(vbkkt, gpu_lib, lp)
+    Kf = H.kkt_for(vbkkt, gpu_lib, lp, mode=vbkkt.MODE_FAST)
+    try:
+        Ks.factor(E, D)
+        Kf.factor(E, D)
+        Ls, ds, ms = Ks.get_factor()
+        Lf, df, mf = Kf.get_factor()
+        T = Kf.dim - Kf.window
+        nsp = int(Kf.kAAt[T])
+        assert T > 0 and nsp > 0
+        assert np.array_equal(Lf[:nsp], Ls[:nsp])
+        assert np.array_equal(df[:T], ds[:T]) and np.array_equal(mf[:T], ms[:T])
+    finally:
+        Ks.close()
+        Kf.close()
+
+
+@pytest.mark.parametrize("R,K", [(8, 5), (12, 8)])
+def test_fast_mode_multicommodity_kkt_step(vbkkt, gpu_lib, R, K):
+    """BASELINE config 3 at sizes the strict mode finishes in seconds: the fast-mode KKT step on the synthetic
+    multicommodity LP leaves a residual at rounding level and agrees with the strict (= reference) solution."""
+    import scipy.sparse as sp
+    lp = vbkkt.workloads.multicommodity_lp(R, K)
+    rng = np.random.default_rng(20)
+    E, D = 10.0 ** rng.uniform(-3, 3, lp.m), 10.0 ** rng.uniform(-3, 3, lp.n)
+    ry, rx = rng.standard_normal(lp.m), rng.standard_normal(lp.n)
+    Ks = H.kkt_for(vbkkt, gpu_lib, lp)
+    Kf = H.kkt_for(vbkkt, gpu_lib, lp, mode=vbkkt.MODE_FAST)
+    try:
+        Ks.factor(E, D); Kf.factor(E, D)
+        sy, sx, _ = Ks.solve(E, D, ry, rx)
+        fy, fx, _ = Kf.solve(E, D, ry, rx)
+        A = sp.csc_matrix((lp.A, lp.iA, lp.kA), shape=(lp.m, lp.n))
+        r1 = -E * fy + A @ fx - ry
+        r2 = A.T @ fy + D * fx - rx
+        scale = max(np.abs(ry).max(), np.abs(rx).max(), np.abs(fy).max(), np.abs(fx).max()) + 1
+        assert max(np.abs(r1).max(), np.abs(r2).max()) <= 1e-8 * scale
+        assert P._rel(fy, sy) < 1e-6 and P._rel(fx, sx) < 1e-6
+        z = np.random.default_rng(R).standard_normal(lp.m + lp.n)
+        assert P._rel(Kf.rawsolve(z), Ks.rawsolve(z)) < 1e-5
+    finally:
+        Ks.close()
+        Kf.close()
+
+
 def _small_lps(vbkkt, count):
     return [vbkkt.workloads.random_sparse_lp(seed=i, m=60, n=120, nnz_per_col=4) for i in range(count)]
 

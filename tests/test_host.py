@@ -71,3 +71,27 @@ def test_numeric_call_without_gpu_fails_loudly(vbkkt, product_lib):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode != 0
     assert "no CUDA device" in r.stderr and "no CPU path" in r.stderr
+
+
+def test_multicommodity_bench_workload(vbkkt, product_lib):
+    """BASELINE config 3 as bench.py builds it: the generator is deterministic, the synthetic iterate is
+    reproducible, and the symbolic counts stored for the reference arm (bench.MCF_KNOWN) are what the
+    bit-exact symbolic phase finds (host only, no GPU)."""
+    import importlib.util
+    root = vbkkt.PKG_DIR.parent
+    spec = importlib.util.spec_from_file_location("bench_for_test", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    lp, it = bench.mcf_workload("mcf:4:3")
+    lp2, it2 = bench.mcf_workload("mcf:4:3")
+    V, E = 16, 48
+    assert (lp.m, lp.n, lp.nz) == (2 * 3 * V + E, 3 * E, 5 * 3 * E)
+    assert np.array_equal(lp.A, lp2.A) and np.array_equal(lp.iA, lp2.iA) and np.array_equal(it["E"], it2["E"])
+    assert it["E"].shape == (lp.m,) and it["D"].shape == (lp.n,) and (it["E"] > 0).all() and (it["D"] > 0).all()
+    lp, _ = bench.mcf_workload("mcf:20:12")
+    kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    k = vbkkt.KKT(device=-1, lib=product_lib)
+    k.analyze(lp.n, lp.m, kAt, iAt, At, lp.kA, lp.iA, lp.A)
+    narth, lnz = bench.MCF_KNOWN[(20, 12)]
+    assert k.lnz == lnz and abs(k.narth - narth) <= 1e-3 * narth
+    k.close()
