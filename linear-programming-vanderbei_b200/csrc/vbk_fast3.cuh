@@ -201,6 +201,90 @@ __device__ double panel_rare_pivot(const DenseArgs& a, int b0, int nbb, int c, d
     return (a.perm[a.T + a.p + b0 + c] < a.n_ld ? -1 : 1) * sub;
 }
 
+// LDL^T of one 32 x 32 sub-block of k_panel_diag by warp 0, row `lane` in the lane's registers.  kRare = false: no
+// dependent-pivot branch, returns whether some pivot failed the test (the caller then repeats the sub-block with
+// kRare = true); finished columns are parked as a = l*d at park[lane * park_ld + c].
+template <bool kRare>
+__device__ __forceinline__ bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, double* park, int park_ld,
+                                            double* sd, double* sinv, int* skeep, double* wm, double* colbuf, double* red,
+                                            volatile int* s_cmd)
+{
+    bool bad = false;
+    // rows past a partial sub-block are padded with unit pivots (d = 1, nothing below them): the column
+    // loop below is then branch-free apart from the rare path, whatever nbb is
+    double ar[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+        ar[j] = (lane < nbb && j <= lane) ? blk[(b0 + lane) * kLDD + b0 + j] : ((lane >= nbb && j == lane) ? 1.0 : 0.0);
+    double wmr = (lane < nbb) ? wm[b0 + lane] : 0.0;
+    // Column c of the current matrix is broadcast through a small shared-memory buffer (three copies in
+    // rotation, 16-byte aligned): one 8-byte store per lane, then every lane reads the pivot, and the
+    // a_{j,c} it needs two at a time.  (A shuffle per (c, j) pair made the unrolled loop 60 KB of code --
+    // twice the instruction cache -- and ran at 480 cycles per column; shuffles for the pivot alone were no
+    // faster than the shared-memory round trip, profiles/r01_summary.md.)
+    // The loop is software-pipelined by hand, because a warp issues in order: as soon as column c has
+    // updated a_{.,c+1} (ONE fma per lane), column c+1 is published and its pivot's reciprocal started; the
+    // other 30 - c updates of column c then fill that latency.  Dependent chain per column: fma, store,
+    // load, reciprocal (one MUFU + five fma, no slow-path call), multiply.
+    double d, magc, inv, nxt;
+    {
+        double* cb = colbuf;
+        cb[lane] = ar[0];
+        cb[32 + lane] = wmr;
+        __syncwarp();
+        d = cb[0]; magc = cb[32]; nxt = cb[1];
+        inv = vbk_rcp_fast(d);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const double* cb = colbuf + (c % 3) * 64;
+        const double arc = ar[c];                                      // a_{r,c} = l_{r,c} d_c   (lanes r > c)
+        int keep = 1;
+        if (!kRare) bad = bad || (fabs(d) <= a.tol * magc);
+        if (kRare && __builtin_expect(fabs(d) <= a.tol * magc, 0)) {   // uniform over the warp; ldlt.c:600-614
+            const double nd = panel_rare_pivot(a, b0, nbb, c, (lane > c && lane < nbb) ? fabs(arc) : 0.0, magc,
+                                               blk, sd, sinv, skeep, red, s_cmd);
+            if (nd != 0.0) { d = nd; inv = vbk_rcp(d); }               // substituted pivot
+            else { keep = 0; inv = 0.0; }                              // dependent row: dropped
+        }
+        const double lr = arc * inv;                                   // l_{r,c}
+        const bool mine = lane == c && c < nbb, below = lane > c && lane < nbb;
+        if (mine) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
+        if (below) park[lane * park_ld + c] = arc;                     // parked as l*d
+        const double term = fabs(lr * arc);                            // what this column adds to a_{r,r}
+        wmr = (below && term > wmr) ? term : wmr;
+        // a_{r,j} -= l_{r,c} d_c l_{j,c} = lr * a_{j,c}   (meaningful for r >= j; the rest is never read)
+        if (c + 1 < 32) {
+            ar[c + 1] = fma(-lr, nxt, ar[c + 1]);                      // column c+1 is final now: publish it
+            double* cn = colbuf + ((c + 1) % 3) * 64;
+            cn[lane] = ar[c + 1];
+            cn[32 + lane] = wmr;
+            __syncwarp();
+            d = cn[c + 1]; magc = cn[32 + c + 1]; nxt = (c + 2 < 32) ? cn[c + 2] : 0.0;
+            inv = vbk_rcp_fast(d);
+            // the rest of column c's update, in the shadow of that reciprocal
+            if (c & 1) {                                               // c + 2 odd
+                if (c + 2 < 32) ar[c + 2] = fma(-lr, cb[c + 2], ar[c + 2]);
+#pragma unroll
+                for (int j = c + 3; j < 32; j += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(cb + j);
+                    ar[j] = fma(-lr, v.x, ar[j]);
+                    ar[j + 1] = fma(-lr, v.y, ar[j + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int j = c + 2; j < 32; j += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(cb + j);
+                    ar[j] = fma(-lr, v.x, ar[j]);
+                    ar[j + 1] = fma(-lr, v.y, ar[j + 1]);
+                }
+            }
+        }
+    }
+    if ((kRare || !bad) && lane < nbb) wm[b0 + lane] = wmr;
+    return bad;
+}
+
 static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
 {
     VBK_DYN_SMEM(raw);
@@ -252,88 +336,16 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         // and the scaling pass below expect).  The other warps wait in a command loop and only help in the rare
         // dependent-pivot path (reference ldlt.c:600-614), which needs max |column| over all rows below.
         if (warp == 0) {
-            // rows past a partial sub-block are padded with unit pivots (d = 1, nothing below them): the column
-            // loop below is then branch-free apart from the rare path, whatever nbb is
-            double ar[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                ar[j] = (lane < nbb && j <= lane) ? blk[(b0 + lane) * kLDD + b0 + j] : ((lane >= nbb && j == lane) ? 1.0 : 0.0);
-            double wmr = (lane < nbb) ? wm[b0 + lane] : 0.0;
-            if (ar[31] == 123.456) wmr += 1.0;                                 // (keeps the loads ahead of the tick)
-            panel_tick(a, 5, &tk);
-            // Column c of the current matrix is broadcast through a small shared-memory buffer (three copies in
-            // rotation, 16-byte aligned): one 8-byte store per lane, then every lane reads the pivot, and the
-            // a_{j,c} it needs two at a time.  (A shuffle per (c, j) pair made the unrolled loop 60 KB of code --
-            // twice the instruction cache -- and ran at 480 cycles per column; shuffles for the pivot alone were no
-            // faster than the shared-memory round trip, profiles/r01_summary.md.)
-            // The loop is software-pipelined by hand, because a warp issues in order: as soon as column c has
-            // updated a_{.,c+1} (ONE fma per lane), column c+1 is published and its pivot's reciprocal started; the
-            // other 30 - c updates of column c then fill that latency.  Dependent chain per column: fma, store,
-            // load, reciprocal (one MUFU + five fma, no slow-path call), multiply.
-            double d, magc, inv, nxt;
-            {
-                double* cb = colbuf;
-                cb[lane] = ar[0];
-                cb[32 + lane] = wmr;
-                __syncwarp();
-                d = cb[0]; magc = cb[32]; nxt = cb[1];
-                inv = vbk_rcp_fast(d);
+            // optimistic pass without the dependent-pivot branch (its columns are parked in wbuf, which phase (b) only
+            // fills later); if a pivot failed the test, the sub-block -- still untouched in blk -- is redone with the
+            // full rule.  The branch and the call behind it cost 145 of 290 cycles per column (profiles/r01_summary.md).
+            const bool bad = panel_ldl32<false>(a, b0, nbb, lane, blk, wbuf, 33, sd, sinv, skeep, wm, colbuf, red, s_cmd);
+            if (bad) panel_ldl32<true>(a, b0, nbb, lane, blk, blk + b0 * kLDD + b0, kLDD, sd, sinv, skeep, wm, colbuf, red, s_cmd);
+            else {
+#pragma unroll 8
+                for (int c = 0; c < 31; ++c)
+                    if (lane > c && lane < nbb) blk[(b0 + lane) * kLDD + b0 + c] = wbuf[lane * 33 + c];
             }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const double* cb = colbuf + (c % 3) * 64;
-                const double arc = ar[c];                                      // a_{r,c} = l_{r,c} d_c   (lanes r > c)
-                int keep = 1;
-#ifdef VBK_X1
-                if (false) {
-#else
-                if (__builtin_expect(fabs(d) <= a.tol * magc, 0)) {            // uniform over the warp; ldlt.c:600-614
-#endif
-                    const double nd = panel_rare_pivot(a, b0, nbb, c, (lane > c && lane < nbb) ? fabs(arc) : 0.0, magc,
-                                                       blk, sd, sinv, skeep, red, s_cmd);
-                    if (nd != 0.0) { d = nd; inv = vbk_rcp(d); }               // substituted pivot
-                    else { keep = 0; inv = 0.0; }                              // dependent row: dropped
-                }
-                const double lr = arc * inv;                                   // l_{r,c}
-                const bool mine = lane == c && c < nbb, below = lane > c && lane < nbb;
-#ifndef VBK_X2
-                if (mine) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
-                if (below) blk[(b0 + lane) * kLDD + b0 + c] = arc;             // parked as l*d
-                const double term = fabs(lr * arc);                            // what this column adds to a_{r,r}
-                wmr = (below && term > wmr) ? term : wmr;
-#else
-                if (mine) { sinv[b0 + c] = inv; }
-#endif
-                // a_{r,j} -= l_{r,c} d_c l_{j,c} = lr * a_{j,c}   (meaningful for r >= j; the rest is never read)
-                if (c + 1 < 32) {
-                    ar[c + 1] = fma(-lr, nxt, ar[c + 1]);                      // column c+1 is final now: publish it
-                    double* cn = colbuf + ((c + 1) % 3) * 64;
-                    cn[lane] = ar[c + 1];
-                    cn[32 + lane] = wmr;
-                    __syncwarp();
-                    d = cn[c + 1]; magc = cn[32 + c + 1]; nxt = (c + 2 < 32) ? cn[c + 2] : 0.0;
-                    inv = vbk_rcp_fast(d);
-                    // the rest of column c's update, in the shadow of that reciprocal
-                    if (c & 1) {                                               // c + 2 odd
-                        if (c + 2 < 32) ar[c + 2] = fma(-lr, cb[c + 2], ar[c + 2]);
-#pragma unroll
-                        for (int j = c + 3; j < 32; j += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(cb + j);
-                            ar[j] = fma(-lr, v.x, ar[j]);
-                            ar[j + 1] = fma(-lr, v.y, ar[j + 1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = c + 2; j < 32; j += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(cb + j);
-                            ar[j] = fma(-lr, v.x, ar[j]);
-                            ar[j + 1] = fma(-lr, v.y, ar[j + 1]);
-                        }
-                    }
-                }
-            }
-            panel_tick(a, b0 == 0 ? 13 : 6, &tk);
-            if (lane < nbb) wm[b0 + lane] = wmr;
             if (lane == 0) *s_cmd = -1;
             __syncthreads();                                                   // A: releases the helpers
         } else {

@@ -69,6 +69,8 @@ Kkt::~Kkt()
     if (pin_cnt_) cudaFreeHost(pin_cnt_);
     if (ev_f0_) cudaEventDestroy(ev_f0_);
     if (ev_f1_) cudaEventDestroy(ev_f1_);
+    if (ev_sp0_) cudaEventDestroy(ev_sp0_);
+    if (ev_sp1_) cudaEventDestroy(ev_sp1_);
     for (int u = 0; u < 2; ++u) {
         if (ev_rows_[u]) cudaEventDestroy(ev_rows_[u]);
         if (ev_updb_[u]) cudaEventDestroy(ev_updb_[u]);

@@ -148,6 +148,9 @@ private:
     DevArray<int> sp_end_, sp_lvlcol_;          // fast sparse columns (vbk_fast6.cuh): sparse prefix ends, columns by level
     std::vector<int> sp_lvlptr_;
     int sp_cap_ = 2, sp_cap_heavy_ = 2;
+    int sparse_tuned_ = 0;                      // 0, 1: measuring the two sparse-column paths; 2: decided
+    float sparse_ms_[2] = {0.f, 0.f};           // [0] task kernel, [1] level kernels
+    cudaEvent_t ev_sp0_ = nullptr, ev_sp1_ = nullptr;
     DevArray<double> tinv_, tri_racc_;          // inverted diagonal blocks + slice accumulators of the 128-row sweeps (vbk_fast5.cuh)
     DevArray<unsigned long long> panel_prof_;
     // look-ahead: the bulk of a panel's trailing update runs on a second stream while the next panel is factorised

@@ -13,6 +13,7 @@ void Kkt::prepare_fast()
 {
     const int N = sym_.N, T = sym_.dense_start, W = N - T;
     fast_ready_ = false;
+    sparse_tuned_ = 0;
     if (W <= 0) return;
     if (const char* e = std::getenv("VBK_PANEL")) panel_nb_ = std::max(1, std::min(kPanelMax, std::atoi(e)));
     else panel_nb_ = kPanelMax;
@@ -79,8 +80,9 @@ void Kkt::prepare_fast()
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdPipeSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128>::kSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64>::kSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 128>::kSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 64>::kSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64, 64>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_schur_window2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
@@ -116,7 +118,24 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     const size_t sp_smem = (size_t)kSpWarps * sp_cap_ * (2 * sizeof(double) + sizeof(int));
     const size_t sph_smem = sizeof(double) * ((size_t)2 * sp_cap_heavy_ + 2 * kSpHeavyBatch + kSpHeavyThreads)
                             + sizeof(int) * ((size_t)sp_cap_heavy_ + W + 2 * kSpHeavyBatch + 2);
-    const bool sparse_levels = !(esp && std::string(esp) == "strict") && sp_smem <= (size_t)smem_optin_ && sph_smem <= (size_t)smem_optin_;
+    const bool levels_ok = sp_smem <= (size_t)smem_optin_ && sph_smem <= (size_t)smem_optin_;
+    // Both paths produce the same bits for the sparse columns, so the choice is a pure timing question and is made by
+    // measurement: the first factorisation of a handle runs the task kernel, the second the level kernels (CUDA
+    // events around this phase, one synchronisation each), every later one whichever was faster.  Deep, thin trees
+    // (pilot87: 99 levels) favour the task kernel's column-level dataflow, shallow wide ones (dfl001, multicommodity)
+    // the level kernels.  $VBK_SPARSE=strict|level pins the choice.
+    bool sparse_levels = levels_ok;
+    int tune_slot = -1;
+    if (esp && std::string(esp) == "strict") sparse_levels = false;
+    else if (esp && std::string(esp) == "level") sparse_levels = levels_ok;
+    else if (levels_ok && sparse_tasks > 0 && T > 0) {
+        if (sparse_tuned_ < 2) { tune_slot = sparse_tuned_; sparse_levels = tune_slot == 1; }
+        else sparse_levels = sparse_ms_[1] <= sparse_ms_[0];
+    }
+    if (tune_slot >= 0) {
+        if (!ev_sp0_) { VBK_CUDA(cudaEventCreate(&ev_sp0_)); VBK_CUDA(cudaEventCreate(&ev_sp1_)); }
+        VBK_CUDA(cudaEventRecord(ev_sp0_, stream_));
+    }
 #else
     const bool sparse_levels = false;
 #endif
@@ -144,6 +163,16 @@ void Kkt::factor_window_fast(TiledArgs& ta)
                 ++launches;
             }
         }
+    }
+#endif
+#ifndef VBK_EMU
+    if (tune_slot >= 0) {
+        VBK_CUDA(cudaEventRecord(ev_sp1_, stream_));
+        VBK_CUDA(cudaEventSynchronize(ev_sp1_));
+        float ms = 0.f;
+        VBK_CUDA(cudaEventElapsedTime(&ms, ev_sp0_, ev_sp1_));
+        sparse_ms_[tune_slot] = ms;
+        sparse_tuned_ = tune_slot + 1;
     }
 #endif
     // 2. Schur complement of the sparse columns on the window, written densely; no dependencies.
@@ -231,8 +260,8 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         auto launch_update = [&](int tiles, cudaStream_t st, const DenseArgs& d) {
             if (upd == "k") VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, st, d);
             else if (upd == "p") VBK_LAUNCH(k_dense_update_p, dim3(tiles, tiles), 256, kUpdPipeSmem, st, d);
-            else if (upd == "m128") VBK_LAUNCH(k_dense_update_m<128>, dim3(tiles, tiles), UpdMma<128>::kThreads, UpdMma<128>::kSmem, st, d);
-            else VBK_LAUNCH(k_dense_update_m<64>, dim3(2 * tiles, tiles), UpdMma<64>::kThreads, UpdMma<64>::kSmem, st, d);
+            else if (upd == "m128") VBK_LAUNCH((k_dense_update_m<128, 128>), dim3(tiles, tiles), (UpdMma<128, 128>::kThreads), (UpdMma<128, 128>::kSmem), st, d);
+            else VBK_LAUNCH((k_dense_update_m<128, 64>), dim3(2 * tiles, tiles), (UpdMma<128, 64>::kThreads), (UpdMma<128, 64>::kSmem), st, d);
         };
 #endif
         int k = 0, last_b = -1;
@@ -277,6 +306,12 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             last_b = rest > 0 ? k : -1;
             da.rbase = kend; da.cmax = std::min(kend + kPanelW, W);
             const int tr = (below + kStripTD - 1) / kStripTD, tc = (da.cmax - kend + kStripTD - 1) / kStripTD;
+#ifndef VBK_EMU
+            static const bool strip_dfma = std::getenv("VBK_STRIP") && std::string(std::getenv("VBK_STRIP")) == "dfma";
+            if (!strip_dfma && kStripTD == 64)
+                VBK_LAUNCH((k_dense_update_m<64, 64>), dim3(tc, tr), (UpdMma<64, 64>::kThreads), (UpdMma<64, 64>::kSmem), stream_, da);
+            else
+#endif
             VBK_LAUNCH(k_dense_update_strip, dim3(tc, tr), kStripThreads, sizeof(double) * 2 * kPanelMax * kStripTD, stream_, da);
             ++launches;
         }

@@ -347,7 +347,11 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
     // no contribution and stay 0.  The window is limited by memory (W^2 doubles <= 4 GiB) and by
     // work (dense flops W^3/3 at most 8x the factorisation's own flop count).
     {
-        double rho = 0.25;
+        // default: 0.06 for factorisations that are worth it (>= 1e8 flops: dfl001 7.0 vs 9.4 ms per KKT step, pilot87
+        // 3.7 vs 6.1, multicommodity R=32 39 vs 44 -- the sparse tree loses its deep, heavy top, profiles/r01_summary.md),
+        // 0.25 for small ones, where the window is not what costs time and a narrower tolerance part keeps more of the
+        // reference's arithmetic (the fast-mode sweep over netlib was validated with it)
+        double rho = narth >= 1.0e8 ? 0.06 : 0.25;
         if (const char* e = std::getenv("VBK_WINDOW_RHO")) rho = std::atof(e);
         for (;;) {
             dense_start = N;
