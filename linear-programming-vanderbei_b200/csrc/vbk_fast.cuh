@@ -42,6 +42,7 @@ struct DenseArgs {
     double piv_scale;
     unsigned long long* prof;  // $VBK_PROF: cycle counters of the panel kernels (16 slots), else nullptr
     double* PB;                // packed panel buffer (vbk_fast3.cuh): L11^T, reciprocal pivots, keep flags
+    double* PB2 = nullptr;     // second packed buffer for k_panel_rows_m: off-diagonal blocks, inverted diagonal blocks
     // two-level blocking (vbk_fast2.cuh): the rank-k update takes its k columns S[:, kcol0..kcol0+klen)
     // and P[:, pcol0..pcol0+klen) and touches target rows/columns [rbase, W) x [rbase, cmax)
     int kcol0, klen, pcol0, rbase, cmax;

@@ -47,6 +47,14 @@ constexpr int kPanelBufDoubles = kPanelW * kLDT + 2 * kPanelW;
 constexpr size_t kPanelDiagSmem = sizeof(double) * (kPanelW * kLDD + (kPanelW - 32) * 33 + 3 * kPanelW + kDiagThreads + 192)
                                   + sizeof(int) * (kPanelW + 4);
 constexpr size_t kPanelRowsSmem = sizeof(double) * (kPanelBufDoubles + (kPanelW - 32) * kRowsPerCta) + 16;
+// second packed buffer, for the tensor-path rows kernel (k_panel_rows_m): the six off-diagonal 32 x 32 blocks of L11
+// as MMA "B" operands (block (b, b'), b' < b, element [i * kPB2Ld + j] = L11(32 b + j, 32 b' + i)), the four inverted
+// diagonal blocks ((I + L_bb)^-1 row-major, leading dimension kPB2Ld), reciprocal pivots, keep flags.  kPB2Ld = 36:
+// a fragment load B[t][g] then hits banks 4 t + g.
+constexpr int kPB2Ld = 36;
+constexpr int kPB2Blk = 32 * kPB2Ld;
+constexpr int kPB2Off = 0, kPB2Inv = 6 * kPB2Blk, kPB2Sinv = 10 * kPB2Blk, kPB2Keep = kPB2Sinv + 128;
+constexpr int kPanelBuf2Doubles = kPB2Keep + 128;
 
 #ifndef VBK_EMU
 __device__ __forceinline__ void cp_async8(void* dst, const void* src, bool ok)
@@ -340,6 +348,7 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
             // fills later); if a pivot failed the test, the sub-block -- still untouched in blk -- is redone with the
             // full rule.  The branch and the call behind it cost 145 of 290 cycles per column (profiles/r01_summary.md).
             const bool bad = panel_ldl32<false>(a, b0, nbb, lane, blk, wbuf, 33, sd, sinv, skeep, wm, colbuf, red, s_cmd);
+            if (a.prof && lane == 0) { atomicAdd(&a.prof[14], 1ull); if (bad) atomicAdd(&a.prof[15], 1ull); }
             if (bad) panel_ldl32<true>(a, b0, nbb, lane, blk, blk + b0 * kLDD + b0, kLDD, sd, sinv, skeep, wm, colbuf, red, s_cmd);
             else {
 #pragma unroll 8
@@ -365,6 +374,27 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         __syncthreads();
         panel_tick(a, 1, &tk);
         const int rem = nb - b0 - nbb;
+#ifndef VBK_EMU
+        // (I + L_bb)^-1 for the tensor-path rows kernel, by the last warp (idle in phase (b): at most 96 block rows).
+        // Lane j owns column j: x = e_j, right-looking substitution in registers, L_bb as a broadcast.
+        if (warp == (nt >> 5) - 1) {
+            double x[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) x[u] = (u == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 31; ++kk) {
+                const double xk = x[kk];
+#pragma unroll
+                for (int u = kk + 1; u < 32; ++u) x[u] = fma(-blk[(b0 + u) * kLDD + b0 + kk], xk, x[u]);
+            }
+            // straight to the packed buffer (row-major, coalesced over the lanes); rows past a partial panel: identity
+            if (a.PB2) {
+                double* dst = a.PB2 + kPB2Inv + (b0 >> 5) * kPB2Blk;
+#pragma unroll
+                for (int u = 0; u < 32; ++u) dst[u * kPB2Ld + lane] = (b0 + u < nb) ? x[u] : (u == lane ? 1.0 : 0.0);
+            }
+        }
+#endif
         if (rem <= 0) break;                                                   // uniform
         // ---- (b) block rows below the sub-block: substitution, one thread per row
         for (int t = tid; t < rem; t += nt) {
@@ -388,6 +418,16 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         // t of a fragment takes k = 16 (s / 4) + 4 t + s % 4 in step s (any assignment works as long as both
         // operands use it): with the row strides 129 and 33 a half-warp then reads banks g + 4 t + const -- all
         // different.  nbb == 32 here (a partial sub-block is the last one and has nothing below it).
+        if (a.PB2 && warp == (nt >> 5) - 1) {
+            // the finished off-diagonal blocks L11[b][b'] (b' = this sub-block, b below it) go to the packed buffer of
+            // k_panel_rows_m now, by a warp that owns no output block (at most 6 pairs for 8 warps)
+            const int bp = b0 >> 5;
+            for (int b = bp + 1; b < 4; ++b) {
+                double* dst = a.PB2 + kPB2Off + (b * (b - 1) / 2 + bp) * kPB2Blk;
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) dst[i * kPB2Ld + lane] = blk[(32 * b + lane) * kLDD + b0 + i];   // [i][j] = L(32b + j, 32b' + i)
+            }
+        }
         {
             const int g = lane >> 2, t4 = lane & 3;
             const int nblk = (rem + 31) >> 5, npairs = nblk * (nblk + 1) / 2;
@@ -471,6 +511,11 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         }
         if (lane < kLDT - kPanelW) a.PB[c * kLDT + kPanelW + lane] = 0.0;
     }
+#ifndef VBK_EMU
+    if (a.PB2) {
+        for (int e = tid; e < kPanelW; e += nt) { a.PB2[kPB2Sinv + e] = sinv[e]; a.PB2[kPB2Keep + e] = skeep[e] ? 1.0 : 0.0; }
+    }
+#endif
     for (int e = tid; e < kPanelW; e += nt) {
         a.PB[kPanelW * kLDT + e] = sinv[e];
         a.PB[kPanelW * kLDT + kPanelW + e] = skeep[e] ? 1.0 : 0.0;
@@ -602,6 +647,156 @@ static __global__ void __launch_bounds__(kRowThreads) k_panel_rows(DenseArgs a)
         __syncwarp();
     }
 }
+
+
+#ifndef VBK_EMU
+// rows below the diagonal block on the FP64 tensor path.  With w = l * d the row equation w L11^T = s is solved 32
+// columns at a time:  w_b = (s_b - sum_{b' < b} w_b' L11[b][b']^T) (I + L_bb)^-T  -- products of a 16-row slab with
+// 32 x 32 blocks, all mma.sync.m8n8k4.  A warp owns 16 rows for the whole panel; its w (the next products' "A"
+// operand) and the accumulator it has to turn into an operand go through a per-warp shared-memory slab (leading
+// dimension 132: fragment loads hit banks 4 g + t).  The blocks arrive as ONE bulk asynchronous copy of the packed
+// buffer k_panel_diag leaves behind (kPanelBuf2Doubles).  Same outputs as k_panel_rows: L21 in place, P = L21 D,
+// trailing diagonal and its largest term.
+constexpr int kRowsMWarps = 4;
+constexpr int kRowsMLd = 132;
+constexpr size_t kPanelRowsMSmem = sizeof(double) * (kPanelBuf2Doubles + kRowsMWarps * 16 * kRowsMLd) + 16;
+
+static __global__ void __launch_bounds__(kRowsMWarps * 32) k_panel_rows_m(DenseArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    double* pb = reinterpret_cast<double*>(raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    double* wsl = pb + kPanelBuf2Doubles + warp * 16 * kRowsMLd;          // this warp's 16 x 128 slab
+    const int nb = a.nb, p = a.p;
+    {
+        unsigned long long* mbar = reinterpret_cast<unsigned long long*>(pb + kPanelBuf2Doubles + kRowsMWarps * 16 * kRowsMLd);
+        const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(mbar);
+        const unsigned dst_s = (unsigned)__cvta_generic_to_shared(pb);
+        constexpr unsigned kBytes = (unsigned)(sizeof(double) * kPanelBuf2Doubles);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(kBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst_s), "l"(a.PB2), "r"(kBytes), "r"(mbar_s) : "memory");
+        }
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(mbar_s), "r"(0u) : "memory");
+        }
+    }
+    const double* sinv = pb + kPB2Sinv;
+    const double* keepd = pb + kPB2Keep;
+    const int nslabs = (a.W - p - nb + 15) / 16;
+    for (int sl = blockIdx.x * kRowsMWarps + warp; sl < nslabs; sl += gridDim.x * kRowsMWarps) {
+        const int r0 = p + nb + sl * 16;
+        // the slab of S21: rows r0 + i, columns p + c  ->  wsl[i][c]   (lane = row pair / column: coalesced over rows)
+        for (int e = lane; e < 16 * kPanelW; e += 32) {
+            const int i = e & 15, c = e >> 4;
+            wsl[i * kRowsMLd + c] = (r0 + i < a.W && c < nb) ? SW(a, r0 + i, p + c) : 0.0;
+        }
+        __syncwarp();
+        double dsum[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, dabs[2][2] = {{0.0, 0.0}, {0.0, 0.0}};    // [m tile][row half]: rows g (both), see below
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            // acc = s_b as C fragments: C[g][2t + j] of m tile mi (rows 8 mi + g), n tile ni (columns 32 b + 8 ni + 2t + j)
+            double acc[2][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) acc[mi][ni][j] = wsl[(8 * mi + g) * kRowsMLd + 32 * b + 8 * ni + 2 * t + j];
+            // minus the earlier sub-blocks' w times L11[b][b']^T
+#pragma unroll
+            for (int bp = 0; bp < b; ++bp) {
+                const double* Bk = pb + kPB2Off + (b * (b - 1) / 2 + bp) * kPB2Blk;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    double av[2], bv[4];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) av[mi] = -wsl[(8 * mi + g) * kRowsMLd + 32 * bp + 4 * k4 + t];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) bv[ni] = Bk[(4 * k4 + t) * kPB2Ld + 8 * ni + g];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+                }
+            }
+            // the accumulator becomes an operand: through the slab (its s_b columns are consumed)
+            __syncwarp();
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) wsl[(8 * mi + g) * kRowsMLd + 32 * b + 8 * ni + 2 * t + j] = acc[mi][ni][j];
+            __syncwarp();
+            // w_b = acc (I + L_bb)^-T :  C[m][n] = sum_k acc[m][k] Inv[n][k]
+            double wv[2][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) { wv[mi][ni][0] = 0.0; wv[mi][ni][1] = 0.0; }
+            const double* Iv = pb + kPB2Inv + b * kPB2Blk;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                double av[2], bv[4];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) av[mi] = wsl[(8 * mi + g) * kRowsMLd + 32 * b + 4 * k4 + t];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) bv[ni] = Iv[(8 * ni + g) * kPB2Ld + 4 * k4 + t];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma884(wv[mi][ni][0], wv[mi][ni][1], av[mi], bv[ni]);
+            }
+            __syncwarp();
+            // dropped columns give w = l = 0; outputs; w back into the slab for the later sub-blocks
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int c = 32 * b + 8 * ni + 2 * t + j, r = r0 + 8 * mi + g;
+                        const double w = (keepd[c] != 0.0) ? wv[mi][ni][j] : 0.0;
+                        const double l = w * sinv[c];
+                        wsl[(8 * mi + g) * kRowsMLd + c] = w;
+                        if (r < a.W && c < nb) {
+                            SW(a, r, p + c) = l;
+                            a.P[(size_t)r + (size_t)(a.pcol0 + c) * a.W] = w;
+                            const double tt = l * w;
+                            dsum[mi][0] += tt;
+                            dabs[mi][0] = fmax(dabs[mi][0], fabs(tt));
+                        }
+                    }
+            __syncwarp();
+        }
+        // row r0 + 8 mi + g: its four lanes (t = 0..3) hold partial sums
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            double ds = dsum[mi][0], da = dabs[mi][0];
+#pragma unroll
+            for (int sft = 1; sft < 4; sft <<= 1) {
+                ds += __shfl_xor_sync(0xffffffffu, ds, sft);
+                da = fmax(da, __shfl_xor_sync(0xffffffffu, da, sft));
+            }
+            const int r = r0 + 8 * mi + g;
+            if (t == 0 && r < a.W) {
+                SW(a, r, r) -= ds;
+                if (da > a.wmag[r]) a.wmag[r] = da;
+            }
+        }
+        __syncwarp();
+    }
+}
+#endif  // !VBK_EMU
 
 // Look-ahead "A part": rank-klen update of the column strip [rbase, cmax) (at most kPanelW columns: the NEXT panel)
 // for all rows >= rbase.  It sits on the critical path between two panel factorisations, so it is cut into many

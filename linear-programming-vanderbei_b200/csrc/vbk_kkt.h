@@ -143,7 +143,7 @@ private:
     // fast mode (vbk_fast.cuh, vbk_kkt_fast.cu): dense scratch for the trailing window
     bool fast_ready_ = false, light_schur_ = false;
     int panel_nb_ = 32;
-    DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_, panel_buf_;
+    DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_, panel_buf_, panel_buf2_;
     DevArray<int> wmark_, pan_keep_, tri_flags_, tri3_flags_;
     DevArray<int> sp_end_, sp_lvlcol_;          // fast sparse columns (vbk_fast6.cuh): sparse prefix ends, columns by level
     std::vector<int> sp_lvlptr_;

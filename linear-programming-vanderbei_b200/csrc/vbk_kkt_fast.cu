@@ -21,6 +21,9 @@ void Kkt::prepare_fast()
     P_.alloc((size_t)2 * W * kOuterPanel);          // two panels of L21*D: the look-ahead keeps two updates in flight
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
     pan_d_.alloc(kPanelW); pan_keep_.alloc(kPanelW); panel_buf_.alloc(kPanelBufDoubles);
+#ifndef VBK_EMU
+    panel_buf2_.alloc(kPanelBuf2Doubles);
+#endif
     tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
 #ifndef VBK_EMU
     {
@@ -90,6 +93,7 @@ void Kkt::prepare_fast()
     VBK_CUDA(cudaFuncSetAttribute(k_window_tri3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriV3Smem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_panel_rows_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsMSmem));
 #endif
 #ifndef VBK_EMU
     if (!stream2_) {
@@ -264,6 +268,10 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             else VBK_LAUNCH((k_dense_update_m<128, 64>), dim3(2 * tiles, tiles), (UpdMma<128, 64>::kThreads), (UpdMma<128, 64>::kSmem), st, d);
         };
 #endif
+#ifndef VBK_EMU
+        const bool rows_mma = !(std::getenv("VBK_ROWS") && std::string(std::getenv("VBK_ROWS")) == "dfma");
+        da.PB2 = rows_mma ? panel_buf2_.p : nullptr;
+#endif
         int k = 0, last_b = -1;
         for (int P0 = 0; P0 < W; P0 += kPanelW, ++k) {
             da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0;
@@ -272,8 +280,16 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             ++launches;
             const int below = W - P0 - da.nb;
             if (below <= 0) continue;
+#ifndef VBK_EMU
+            if (rows_mma) {
+                const int gm = std::min((below + 16 * kRowsMWarps - 1) / (16 * kRowsMWarps), num_sms_ * 2);
+                VBK_LAUNCH(k_panel_rows_m, gm, kRowsMWarps * 32, kPanelRowsMSmem, stream_, da);
+            } else
+#endif
+            {
             const int g = std::min((below + kRowsPerCta - 1) / kRowsPerCta, num_sms_ * 4);
             VBK_LAUNCH(k_panel_rows, g, kRowThreads, kPanelRowsSmem, stream_, da);
+            }
             ++launches;
             const int kend = P0 + da.nb;
             da.kcol0 = P0; da.klen = da.nb;
@@ -324,8 +340,8 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         panel_prof_.download(h, 16, stream_);
         VBK_CUDA(cudaStreamSynchronize(stream_));
         std::fprintf(stderr, "vbkkt panel profile (cycles of thread 0, CTA 0, summed over %d panels): diag load %llu, warp LDL %llu, "
-                     "(registers %llu, columns of the first sub-block %llu, of the others %llu) block trsm %llu, block update %llu, store %llu | rows: panel fetch %llu, row loads %llu, rank update %llu, "
-                     "stages %llu, stores %llu\n", (W + kPanelW - 1) / kPanelW, h[0], h[1] + h[5] + h[6] + h[13], h[5], h[13], h[6], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
+                     "(%llu sub-blocks, %llu repeated with the full pivot rule) block trsm %llu, block update %llu, store %llu | rows: panel fetch %llu, row loads %llu, rank update %llu, "
+                     "stages %llu, stores %llu\n", (W + kPanelW - 1) / kPanelW, h[0], h[1], h[14], h[15], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
     }
     if (dense_v2) {
         // two-level blocking (vbk_fast2.cuh): inner panels of panel_nb_ columns, one rank-(outer) update of
