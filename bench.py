@@ -643,10 +643,18 @@ def main():
     kname = ("k_factor_tiled (strict)" if a.mode == "strict" else
              "numeric factorisation = k_factor_tiled (sparse columns) + k_schur_window + per 128-column panel "
              "k_panel_diag, k_panel_rows, k_dense_update_strip, k_dense_update_m (DMMA rank-128 update)")
+    # DRAM traffic of one factorisation, measured once under ncu (profiles/r01_traffic.json); null when this workload
+    # or mode has no capture
+    traffic = None
+    tj = ROOT / "profiles" / "r01_traffic.json"
+    if a.mode == "fast" and tj.exists():
+        ent = json.loads(tj.read_text()).get(a.workload.split(":")[0] if a.workload.startswith("mcf") and a.workload in ("mcf", "mcf:32:25") else a.workload)
+        if isinstance(ent, dict):
+            traffic = ent.get("bytes_per_factorisation")
     roofline = {"kernel": kname, "bound": "tensor" if fp64_bound else "hbm",
                 "achieved": fp64["achieved_tflops"] if fp64_bound else hbm["achieved_gbs"],
                 "peak": fp64_peak if fp64_bound else hbm_peak, "unit": "TFLOP/s" if fp64_bound else "GB/s",
-                "frac": fp64["frac"] if fp64_bound else hbm["frac"], "traffic": None,
+                "frac": fp64["frac"] if fp64_bound else hbm["frac"], "traffic": traffic, "algorithmic_bytes": b_fac,
                 "peak_source": fp64["peak_source"] if fp64_bound else peak_src,
                 "flop_per_byte": intensity, "kernel_ms": fac_s * 1e3, "share_of_step": fac_s * 1e3 / ms_per_step,
                 "fp64": fp64, "hbm": hbm,
