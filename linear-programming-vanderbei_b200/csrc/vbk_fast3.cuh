@@ -212,15 +212,10 @@ __device__ double panel_rare_pivot(const DenseArgs& a, int b0, int nbb, int c, d
 // LDL^T of one 32 x 32 sub-block of k_panel_diag by warp 0, row `lane` in the lane's registers.  kRare = false: no
 // dependent-pivot branch, returns whether some pivot failed the test (the caller then repeats the sub-block with
 // kRare = true); finished columns are parked as a = l*d at park[lane * park_ld + c].
-// Out of line on purpose: compiled as a function of its own, the unrolled column loop is scheduled like the
-// stand-alone micro-benchmark (scratch/ubench2.cu, 126 cycles per column); inlined into k_panel_diag it shared the
-// kernel's register allocation and ran at ~300.
+// (Taking this function out of line -- so that it is compiled like the stand-alone micro-benchmark, scratch/ubench2.cu,
+// 127 cycles per column -- did not help: 440 cycles per column, the shared-memory arrays become generic pointers.)
 template <bool kRare>
-#ifdef VBK_EMU
 __device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
 bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, double* park, int park_ld,
                  double* sd, double* sinv, int* skeep, double* wm, double* colbuf, double* red, volatile int* s_cmd)
 {
