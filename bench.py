@@ -431,10 +431,12 @@ def main():
     # strict = bit-exact replay of the reference's rounding order (reported beside it at N=1)
     ap.add_argument("--mode", default="fast", choices=["strict", "fast"])
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode side measurement")
-    ap.add_argument("--batch-per-gpu", type=int, default=8, help="batch workload: LPs per GPU per step")
+    ap.add_argument("--batch-per-gpu", type=int, default=0, help="batch workload: LPs per GPU per step (default: 2 per solver stream, at least 8)")
     ap.add_argument("--batch-m", type=int, default=2000)
     ap.add_argument("--batch-n", type=int, default=4000)
-    ap.add_argument("--streams", type=int, default=4, help="batch workload: solver streams in flight per GPU")
+    # one host thread per stream runs the LP's symbolic phase (1.2 s per m=2000 LP on one core, measured) and its METHOD
+    # loop; the GPU part of such an LP is 0.2-0.4 s, so the batch is bound by host cores: default = cores / ranks
+    ap.add_argument("--streams", type=int, default=0, help="batch workload: solver streams in flight per GPU (default: host cores / ranks, 2..16)")
     ap.add_argument("--grid", type=int, default=100, help="rowblock workload: grid side R")
     ap.add_argument("--commodities", type=int, default=126, help="rowblock workload: K")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -447,6 +449,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if a.workload in ("batch", "rowblock"):
+        if a.streams <= 0:
+            a.streams = max(2, min(16, (os.cpu_count() or 8) // max(world, 1)))
+        if a.batch_per_gpu <= 0:
+            a.batch_per_gpu = max(8, 2 * a.streams)
         return multi_gpu_workload(a, rank, local_rank, world)
 
     lp, it = load_workload(a.workload, a.iterate)

@@ -214,14 +214,31 @@ __device__ double panel_rare_pivot(const DenseArgs& a, int b0, int nbb, int c, d
 // kRare = true); finished columns are parked as a = l*d at park[lane * park_ld + c].
 // (Taking this function out of line -- so that it is compiled like the stand-alone micro-benchmark, scratch/ubench2.cu,
 // 127 cycles per column -- did not help: 440 cycles per column, the shared-memory arrays become generic pointers.)
+// Ordering point between a lane's store into the column ring and the other lanes' loads.  In the optimistic pass the
+// warp runs straight-line code (selects, no branches) from one __syncwarp at entry, so its lanes execute every
+// instruction together and the in-order shared-memory pipe orders the store before the loads; a compiler-level fence
+// is all that is needed.  A real __syncwarp() here costs ~200 cycles per column: the compiler cannot prove convergence,
+// emits a divergence check and re-derives the shared-memory window base (S2UR SR_CgaCtaId) after every one of them,
+// right on the dependent chain (cuobjdump: 33 BRA.DIV + 57 S2UR in the kernel, none in scratch/ubench2.cu, which runs the
+// same loop at 127 cycles per column).  The pass with the rare path (branches, a call) keeps the real barrier.
+template <bool kRare> __device__ __forceinline__ void ldl_fence()
+{
+#ifdef VBK_EMU
+    __syncwarp();
+#else
+    if (kRare) __syncwarp();
+    else asm volatile("" ::: "memory");
+#endif
+}
+
 template <bool kRare>
 __device__ __forceinline__
-bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, double* park, int park_ld,
-                 double* sd, double* sinv, int* skeep, double* wm, double* colbuf, double* red, volatile int* s_cmd)
+bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, double* sd, double* sinv, int* skeep, double* wm,
+                 double* colbuf, double* red, volatile int* s_cmd)
 {
-    bool bad = false;
     // rows past a partial sub-block are padded with unit pivots (d = 1, nothing below them): the column
     // loop below is then branch-free apart from the rare path, whatever nbb is
+    __syncwarp();
     double ar[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -236,21 +253,29 @@ bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, dou
     // updated a_{.,c+1} (ONE fma per lane), column c+1 is published and its pivot's reciprocal started; the
     // other 30 - c updates of column c then fill that latency.  Dependent chain per column: fma, store,
     // load, reciprocal (one MUFU + five fma, no slow-path call), multiply.
-    double d, magc, inv, nxt;
+    // Bookkeeping is kept off that chain in the optimistic pass (kRare = false; scratch/ubench2.cu: 126 cycles per
+    // column bare, 233 with per-column pivot stores + parked column + broadcast term magnitude): the pivot test is
+    // made by the lane that owns the pivot on its own registers and voted on once at the end, pivots and
+    // reciprocals stay in the owning lane's registers, and the finished columns -- a_{r,c} is not touched again
+    // after column c -- are written from the registers after the loop.
+    double d, magc = 0.0, inv, nxt;
+    double myd = 1.0, myinv = 0.0;
+    bool badl = false;
     {
         double* cb = colbuf;
         cb[lane] = ar[0];
-        cb[32 + lane] = wmr;
-        __syncwarp();
-        d = cb[0]; magc = cb[32]; nxt = cb[1];
+        if (kRare) cb[32 + lane] = wmr;
+        ldl_fence<kRare>();
+        d = cb[0]; nxt = cb[1];
+        if (kRare) magc = cb[32];
         inv = vbk_rcp_fast(d);
+        if (!kRare) badl = lane == 0 && fabs(ar[0]) <= a.tol * wmr;
     }
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
         const double* cb = colbuf + (c % 3) * 64;
         const double arc = ar[c];                                      // a_{r,c} = l_{r,c} d_c   (lanes r > c)
         int keep = 1;
-        if (!kRare) bad = bad || (fabs(d) <= a.tol * magc);
         if (kRare && __builtin_expect(fabs(d) <= a.tol * magc, 0)) {   // uniform over the warp; ldlt.c:600-614
             const double nd = panel_rare_pivot(a, b0, nbb, c, (lane > c && lane < nbb) ? fabs(arc) : 0.0, magc,
                                                blk, sd, sinv, skeep, red, s_cmd);
@@ -259,18 +284,22 @@ bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, dou
         }
         const double lr = arc * inv;                                   // l_{r,c}
         const bool mine = lane == c && c < nbb, below = lane > c && lane < nbb;
-        if (mine) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
-        if (below) park[lane * park_ld + c] = arc;                     // parked as l*d
+        if (kRare) {
+            if (mine) { sd[b0 + c] = d; sinv[b0 + c] = inv; skeep[b0 + c] = keep; }
+            if (below) blk[(b0 + lane) * kLDD + b0 + c] = arc;         // parked as l*d (the rare path reads it)
+        } else if (mine) { myd = d; myinv = inv; }
         const double term = fabs(lr * arc);                            // what this column adds to a_{r,r}
         wmr = (below && term > wmr) ? term : wmr;
         // a_{r,j} -= l_{r,c} d_c l_{j,c} = lr * a_{j,c}   (meaningful for r >= j; the rest is never read)
         if (c + 1 < 32) {
             ar[c + 1] = fma(-lr, nxt, ar[c + 1]);                      // column c+1 is final now: publish it
+            if (!kRare) badl = badl || (lane == c + 1 && fabs(ar[c + 1]) <= a.tol * wmr);
             double* cn = colbuf + ((c + 1) % 3) * 64;
             cn[lane] = ar[c + 1];
-            cn[32 + lane] = wmr;
-            __syncwarp();
-            d = cn[c + 1]; magc = cn[32 + c + 1]; nxt = (c + 2 < 32) ? cn[c + 2] : 0.0;
+            if (kRare) cn[32 + lane] = wmr;
+            ldl_fence<kRare>();
+            d = cn[c + 1]; nxt = (c + 2 < 32) ? cn[c + 2] : 0.0;
+            if (kRare) magc = cn[32 + c + 1];
             inv = vbk_rcp_fast(d);
             // the rest of column c's update, in the shadow of that reciprocal
             if (c & 1) {                                               // c + 2 odd
@@ -291,7 +320,17 @@ bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, dou
             }
         }
     }
-    if ((kRare || !bad) && lane < nbb) wm[b0 + lane] = wmr;
+    if (kRare) {
+        if (lane < nbb) wm[b0 + lane] = wmr;
+        return false;
+    }
+    const bool bad = __any_sync(0xffffffffu, badl && lane < nbb);
+    if (!bad) {
+        if (lane < nbb) { sd[b0 + lane] = myd; sinv[b0 + lane] = myinv; skeep[b0 + lane] = 1; wm[b0 + lane] = wmr; }
+#pragma unroll
+        for (int c = 0; c < 31; ++c)
+            if (lane > c && lane < nbb) blk[(b0 + lane) * kLDD + b0 + c] = ar[c];    // as l*d; scaled by the pass below
+    }
     return bad;
 }
 
@@ -346,17 +385,11 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         // and the scaling pass below expect).  The other warps wait in a command loop and only help in the rare
         // dependent-pivot path (reference ldlt.c:600-614), which needs max |column| over all rows below.
         if (warp == 0) {
-            // optimistic pass without the dependent-pivot branch (its columns are parked in wbuf, which phase (b) only
-            // fills later); if a pivot failed the test, the sub-block -- still untouched in blk -- is redone with the
-            // full rule.  The branch and the call behind it cost 145 of 290 cycles per column (profiles/r01_summary.md).
-            const bool bad = panel_ldl32<false>(a, b0, nbb, lane, blk, wbuf, 33, sd, sinv, skeep, wm, colbuf, red, s_cmd);
+            // optimistic pass without the dependent-pivot branch and without per-column bookkeeping; if a pivot failed
+            // the test, the sub-block -- still untouched in blk -- is redone with the full rule.
+            const bool bad = panel_ldl32<false>(a, b0, nbb, lane, blk, sd, sinv, skeep, wm, colbuf, red, s_cmd);
             if (a.prof && lane == 0) { atomicAdd(&a.prof[14], 1ull); if (bad) atomicAdd(&a.prof[15], 1ull); }
-            if (bad) panel_ldl32<true>(a, b0, nbb, lane, blk, blk + b0 * kLDD + b0, kLDD, sd, sinv, skeep, wm, colbuf, red, s_cmd);
-            else {
-#pragma unroll 8
-                for (int c = 0; c < 31; ++c)
-                    if (lane > c && lane < nbb) blk[(b0 + lane) * kLDD + b0 + c] = wbuf[lane * 33 + c];
-            }
+            if (bad) panel_ldl32<true>(a, b0, nbb, lane, blk, sd, sinv, skeep, wm, colbuf, red, s_cmd);
             if (lane == 0) *s_cmd = -1;
             __syncthreads();                                                   // A: releases the helpers
         } else {

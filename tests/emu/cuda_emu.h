@@ -122,6 +122,11 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
 }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl_from(v, (int)((threadIdx.x % 32) ^ m)); }
 
+inline int __any_sync(unsigned, int pred) {
+    int v = pred ? 1 : 0;
+    for (int m = 16; m > 0; m >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
