@@ -214,6 +214,27 @@ __device__ double panel_rare_pivot(const DenseArgs& a, int b0, int nbb, int c, d
 // kRare = true); finished columns are parked as a = l*d at park[lane * park_ld + c].
 // (Taking this function out of line -- so that it is compiled like the stand-alone micro-benchmark, scratch/ubench2.cu,
 // 127 cycles per column -- did not help: 440 cycles per column, the shared-memory arrays become generic pointers.)
+#ifndef VBK_EMU
+// (I + L_bb)^-1 of the finished 32 x 32 sub-block starting at column bs of the panel, for the tensor-path rows kernel:
+// one warp, lane j owns column j (x = e_j, right-looking substitution in registers, L_bb as a broadcast), result straight
+// to the packed buffer (row-major, coalesced over the lanes); rows past a partial panel: identity.
+__device__ __forceinline__ void panel_inverse32(const DenseArgs& a, const double* blk, int bs, int lane)
+{
+    double x[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) x[u] = (u == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 31; ++kk) {
+        const double xk = x[kk];
+#pragma unroll
+        for (int u = kk + 1; u < 32; ++u) x[u] = fma(-blk[(bs + u) * kLDD + bs + kk], xk, x[u]);
+    }
+    double* dst = a.PB2 + kPB2Inv + (bs >> 5) * kPB2Blk;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) dst[u * kPB2Ld + lane] = (bs + u < a.nb) ? x[u] : (u == lane ? 1.0 : 0.0);
+}
+#endif
+
 // Ordering point between a lane's store into the column ring and the other lanes' loads.  In the optimistic pass the
 // warp runs straight-line code (selects, no branches) from one __syncwarp at entry, so its lanes execute every
 // instruction together and the in-order shared-memory pipe orders the store before the loads; a compiler-level fence
@@ -393,6 +414,10 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
             if (lane == 0) *s_cmd = -1;
             __syncthreads();                                                   // A: releases the helpers
         } else {
+#ifndef VBK_EMU
+            // the last warp inverts the PREVIOUS sub-block while warp 0 factorises this one (nobody waits for it)
+            if (a.PB2 && warp == (nt >> 5) - 1 && b0 > 0) panel_inverse32(a, blk, b0 - 32, lane);
+#endif
             for (;;) {
                 __syncthreads();                                               // A
                 const int cmd = *s_cmd;
@@ -409,27 +434,6 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         __syncthreads();
         panel_tick(a, 1, &tk);
         const int rem = nb - b0 - nbb;
-#ifndef VBK_EMU
-        // (I + L_bb)^-1 for the tensor-path rows kernel, by the last warp (idle in phase (b): at most 96 block rows).
-        // Lane j owns column j: x = e_j, right-looking substitution in registers, L_bb as a broadcast.
-        if (warp == (nt >> 5) - 1) {
-            double x[32];
-#pragma unroll
-            for (int u = 0; u < 32; ++u) x[u] = (u == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 31; ++kk) {
-                const double xk = x[kk];
-#pragma unroll
-                for (int u = kk + 1; u < 32; ++u) x[u] = fma(-blk[(b0 + u) * kLDD + b0 + kk], xk, x[u]);
-            }
-            // straight to the packed buffer (row-major, coalesced over the lanes); rows past a partial panel: identity
-            if (a.PB2) {
-                double* dst = a.PB2 + kPB2Inv + (b0 >> 5) * kPB2Blk;
-#pragma unroll
-                for (int u = 0; u < 32; ++u) dst[u * kPB2Ld + lane] = (b0 + u < nb) ? x[u] : (u == lane ? 1.0 : 0.0);
-            }
-        }
-#endif
         if (rem <= 0) break;                                                   // uniform
         // ---- (b) block rows below the sub-block: substitution, one thread per row
         for (int t = tid; t < rem; t += nt) {
@@ -538,13 +542,17 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
         panel_tick(a, 3, &tk);
     }
     __syncthreads();
+#ifndef VBK_EMU
+    if (a.PB2 && warp == (nt >> 5) - 1) panel_inverse32(a, blk, ((nb - 1) >> 5) << 5, lane);     // the last sub-block's
+#endif
+    const bool want_pb = a.PB2 == nullptr;                          // packed copy for the DFMA rows kernel (k_panel_rows) only
     for (int c = warp; c < kPanelW; c += (nt >> 5)) {
         for (int r = lane; r < kPanelW; r += 32) {
             const double v = (r > c && r < nb) ? blk[r * kLDD + c] : 0.0;
             if (r > c && r < nb) SW(a, p + r, p + c) = v;
-            a.PB[c * kLDT + r] = v;                                 // packed copy for k_panel_rows
+            if (want_pb) a.PB[c * kLDT + r] = v;
         }
-        if (lane < kLDT - kPanelW) a.PB[c * kLDT + kPanelW + lane] = 0.0;
+        if (want_pb && lane < kLDT - kPanelW) a.PB[c * kLDT + kPanelW + lane] = 0.0;
     }
 #ifndef VBK_EMU
     if (a.PB2) {
@@ -552,8 +560,10 @@ static __global__ void __launch_bounds__(kDiagThreads) k_panel_diag(DenseArgs a)
     }
 #endif
     for (int e = tid; e < kPanelW; e += nt) {
-        a.PB[kPanelW * kLDT + e] = sinv[e];
-        a.PB[kPanelW * kLDT + kPanelW + e] = skeep[e] ? 1.0 : 0.0;
+        if (want_pb) {
+            a.PB[kPanelW * kLDT + e] = sinv[e];
+            a.PB[kPanelW * kLDT + kPanelW + e] = skeep[e] ? 1.0 : 0.0;
+        }
         if (e < nb) {
             a.dvec[p + e] = sd[e];
             a.wmark[p + e] = skeep[e];
