@@ -46,6 +46,8 @@ struct DenseArgs {
     // two-level blocking (vbk_fast2.cuh): the rank-k update takes its k columns S[:, kcol0..kcol0+klen)
     // and P[:, pcol0..pcol0+klen) and touches target rows/columns [rbase, W) x [rbase, cmax)
     int kcol0, klen, pcol0, rbase, cmax;
+    // split look-ahead (vbk_kkt_fast.cu): rows skipped below rbase by the tensor-path update, slab range of k_panel_rows_m
+    int rskip = 0, slab_lo = 0, slab_hi = 0x7fffffff;
 };
 
 __device__ __forceinline__ double& SW(const DenseArgs& a, int r, int c) { return a.S[(size_t)r + (size_t)c * a.ld]; }

@@ -736,8 +736,9 @@ static __global__ void __launch_bounds__(kRowsMWarps * 32) k_panel_rows_m(DenseA
     }
     const double* sinv = pb + kPB2Sinv;
     const double* keepd = pb + kPB2Keep;
-    const int nslabs = (a.W - p - nb + 15) / 16;
-    for (int sl = blockIdx.x * kRowsMWarps + warp; sl < nslabs; sl += gridDim.x * kRowsMWarps) {
+    const int nslabs_all = (a.W - p - nb + 15) / 16;
+    const int nslabs = nslabs_all < a.slab_hi ? nslabs_all : a.slab_hi;
+    for (int sl = a.slab_lo + blockIdx.x * kRowsMWarps + warp; sl < nslabs; sl += gridDim.x * kRowsMWarps) {
         const int r0 = p + nb + sl * 16;
         // the slab of S21: rows r0 + i, columns p + c  ->  wsl[i][c]   (lane = row pair / column: coalesced over rows)
         for (int e = lane; e < 16 * kPanelW; e += 32) {

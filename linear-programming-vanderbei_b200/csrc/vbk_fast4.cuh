@@ -187,8 +187,8 @@ static __global__ void __launch_bounds__(UpdMma<TM, TN>::kThreads, 256 / UpdMma<
     VBK_DYN_SMEM(raw);
     double* sm = reinterpret_cast<double*>(raw);            // [stage][A: kUpKC x kLdA | B: kUpKC x kLdB]
     const int tr = blockIdx.y, tc = blockIdx.x;
-    const int r0 = a.rbase + tr * TM, c0 = a.rbase + tc * TN;
-    if (r0 + TM <= c0 || c0 >= a.cmax) return;             // tile entirely above the diagonal / outside
+    const int r0 = a.rbase + a.rskip + tr * TM, c0 = a.rbase + tc * TN;
+    if (r0 + TM <= c0 || c0 >= a.cmax || r0 >= a.W) return;             // tile entirely above the diagonal / outside
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp % (TM / U::kWR)) * U::kWR, wn = (warp / (TM / U::kWR)) * 32;   // this warp's corner of the tile

@@ -74,9 +74,14 @@ Kkt::~Kkt()
     for (int u = 0; u < 2; ++u) {
         if (ev_rows_[u]) cudaEventDestroy(ev_rows_[u]);
         if (ev_updb_[u]) cudaEventDestroy(ev_updb_[u]);
+        if (ev_diag_[u]) cudaEventDestroy(ev_diag_[u]);
+        if (ev_rowsa_[u]) cudaEventDestroy(ev_rowsa_[u]);
+        if (ev_rowsb_[u]) cudaEventDestroy(ev_rowsb_[u]);
+        if (ev_stripb_[u]) cudaEventDestroy(ev_stripb_[u]);
     }
 #ifndef VBK_EMU
     if (stream2_) cudaStreamDestroy(stream2_);
+    if (stream3_) cudaStreamDestroy(stream3_);
     if (stream_) cudaStreamDestroy(stream_);
 #endif
 }

@@ -154,7 +154,8 @@ private:
     DevArray<double> tinv_, tri_racc_;          // inverted diagonal blocks + slice accumulators of the 128-row sweeps (vbk_fast5.cuh)
     DevArray<unsigned long long> panel_prof_;
     // look-ahead: the bulk of a panel's trailing update runs on a second stream while the next panel is factorised
-    cudaStream_t stream2_ = 0;
+    cudaStream_t stream2_ = 0, stream3_ = 0;
+    cudaEvent_t ev_diag_[2] = {nullptr, nullptr}, ev_rowsa_[2] = {nullptr, nullptr}, ev_rowsb_[2] = {nullptr, nullptr}, ev_stripb_[2] = {nullptr, nullptr};
     cudaEvent_t ev_rows_[2] = {nullptr, nullptr}, ev_updb_[2] = {nullptr, nullptr};
     void prepare_fast();
     void factor_window_fast(TiledArgs& ta);

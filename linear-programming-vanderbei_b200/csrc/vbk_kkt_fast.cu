@@ -22,7 +22,7 @@ void Kkt::prepare_fast()
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
     pan_d_.alloc(kPanelW); pan_keep_.alloc(kPanelW); panel_buf_.alloc(kPanelBufDoubles);
 #ifndef VBK_EMU
-    panel_buf2_.alloc(kPanelBuf2Doubles);
+    panel_buf2_.alloc((size_t)2 * kPanelBuf2Doubles);
 #endif
     tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
 #ifndef VBK_EMU
@@ -98,7 +98,12 @@ void Kkt::prepare_fast()
 #ifndef VBK_EMU
     if (!stream2_) {
         VBK_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+        VBK_CUDA(cudaStreamCreateWithFlags(&stream3_, cudaStreamNonBlocking));
         for (int u = 0; u < 2; ++u) {
+            VBK_CUDA(cudaEventCreateWithFlags(&ev_diag_[u], cudaEventDisableTiming));
+            VBK_CUDA(cudaEventCreateWithFlags(&ev_rowsa_[u], cudaEventDisableTiming));
+            VBK_CUDA(cudaEventCreateWithFlags(&ev_rowsb_[u], cudaEventDisableTiming));
+            VBK_CUDA(cudaEventCreateWithFlags(&ev_stripb_[u], cudaEventDisableTiming));
             VBK_CUDA(cudaEventCreateWithFlags(&ev_rows_[u], cudaEventDisableTiming));
             VBK_CUDA(cudaEventCreateWithFlags(&ev_updb_[u], cudaEventDisableTiming));
         }
@@ -272,6 +277,87 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         const bool rows_mma = !(std::getenv("VBK_ROWS") && std::string(std::getenv("VBK_ROWS")) == "dfma");
         da.PB2 = rows_mma ? panel_buf2_.p : nullptr;
 #endif
+#ifndef VBK_EMU
+        // Split look-ahead.  Only the 128 x 128 diagonal tile of panel k+1 stands between two panel factorisations:
+        // it needs the first 128 rows of rows_k and one tile of the strip update.  Everything else of rows_k and of the
+        // strip runs on a third stream while panel k+1 is being factorised (41 us of work under a 58 us kernel on
+        // dfl001), so the dependent chain per panel is diag -> 8 slabs of rows -> 4 tiles -> diag.
+        //   main:  diag_k, rowsA_k (waits stripB_{k-1}), stripA_k (waits B_{k-1})
+        //   sC:    rowsB_k (waits diag_k), stripB_k (waits rowsA_k, B_{k-1})
+        //   sB:    B_k (waits rowsA_k, rowsB_k)
+        // Buffers written by diag_{k+1} / rows_{k+1} while sC still reads: P and the packed operand buffer alternate.
+        // Measured on dfl001 (profiles/r01_summary.md): results identical, KKT step 7.03 ms with the split against 6.80 ms
+        // without -- the four cross-stream event hand-offs per panel cost more than the 41 us they take off the chain.
+        // Kept behind $VBK_SPLIT=1 (a single-kernel panel chain with in-kernel flags is the way to collect this).
+        const bool split = lookahead && rows_mma && kStripTD == 64 && stream3_ != nullptr
+                           && std::getenv("VBK_SPLIT") && std::getenv("VBK_SPLIT")[0] == '1';
+        if (split) {
+            cudaStream_t sC = stream3_;
+            int k = 0, prev_b = -1, prev_sb = -1;
+            for (int P0 = 0; P0 < W; P0 += kPanelW, ++k) {
+                const int u = k & 1;
+                da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0; da.rskip = 0; da.slab_lo = 0; da.slab_hi = 0x7fffffff;
+                da.P = P_.p + (size_t)u * W * kOuterPanel;
+                da.PB2 = panel_buf2_.p + (size_t)u * kPanelBuf2Doubles;
+                VBK_LAUNCH(k_panel_diag, 1, kDiagThreads, kPanelDiagSmem, stream_, da);
+                ++launches;
+                const int below = W - P0 - da.nb;
+                if (below <= 0) continue;
+                VBK_CUDA(cudaEventRecord(ev_diag_[u], stream_));
+                const int kend = P0 + da.nb;
+                const int nslabs = (below + 15) / 16, slabsA = std::min(nslabs, kPanelW / 16);
+                // rows: part A on the main stream, part B on sC
+                if (prev_sb >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_stripb_[prev_sb & 1], 0));
+                DenseArgs ra = da; ra.slab_lo = 0; ra.slab_hi = slabsA;
+                VBK_LAUNCH(k_panel_rows_m, std::max(1, (slabsA + kRowsMWarps - 1) / kRowsMWarps), kRowsMWarps * 32, kPanelRowsMSmem, stream_, ra);
+                VBK_CUDA(cudaEventRecord(ev_rowsa_[u], stream_));
+                ++launches;
+                const bool haveB = nslabs > slabsA;
+                if (haveB) {
+                    VBK_CUDA(cudaStreamWaitEvent(sC, ev_diag_[u], 0));
+                    DenseArgs rb = da; rb.slab_lo = slabsA; rb.slab_hi = 0x7fffffff;
+                    const int gm = std::min((nslabs - slabsA + kRowsMWarps - 1) / kRowsMWarps, num_sms_ * 2);
+                    VBK_LAUNCH(k_panel_rows_m, gm, kRowsMWarps * 32, kPanelRowsMSmem, sC, rb);
+                    VBK_CUDA(cudaEventRecord(ev_rowsb_[u], sC));
+                    ++launches;
+                }
+                da.kcol0 = P0; da.klen = da.nb;
+                // bulk update B_k on sB
+                const int rest = W - (kend + kPanelW);
+                if (rest > 0) {
+                    VBK_CUDA(cudaStreamWaitEvent(sB, ev_rowsa_[u], 0));
+                    if (haveB) VBK_CUDA(cudaStreamWaitEvent(sB, ev_rowsb_[u], 0));
+                    DenseArgs db = da;
+                    db.rbase = kend + kPanelW; db.cmax = W;
+                    launch_update((rest + kUpdTD - 1) / kUpdTD, sB, db);
+                    VBK_CUDA(cudaEventRecord(ev_updb_[u], sB));
+                    ++launches;
+                }
+                // strip: diagonal tile of panel k+1 on the main stream, the rows below it on sC
+                if (prev_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[prev_b & 1], 0));
+                DenseArgs sa = da;
+                sa.rbase = kend; sa.cmax = std::min(kend + kPanelW, W); sa.rskip = 0;
+                const int tc = (sa.cmax - kend + kStripTD - 1) / kStripTD;
+                const int trA = std::min((below + kStripTD - 1) / kStripTD, kPanelW / kStripTD);
+                VBK_LAUNCH((k_dense_update_m<64, 64>), dim3(tc, trA), (UpdMma<64, 64>::kThreads), (UpdMma<64, 64>::kSmem), stream_, sa);
+                ++launches;
+                if (below > kPanelW) {
+                    VBK_CUDA(cudaStreamWaitEvent(sC, ev_rowsa_[u], 0));
+                    if (prev_b >= 0) VBK_CUDA(cudaStreamWaitEvent(sC, ev_updb_[prev_b & 1], 0));
+                    DenseArgs sb2 = sa; sb2.rskip = kPanelW;
+                    const int trB = (below - kPanelW + kStripTD - 1) / kStripTD;
+                    VBK_LAUNCH((k_dense_update_m<64, 64>), dim3(tc, trB), (UpdMma<64, 64>::kThreads), (UpdMma<64, 64>::kSmem), sC, sb2);
+                    VBK_CUDA(cudaEventRecord(ev_stripb_[u], sC));
+                    prev_sb = k;
+                    ++launches;
+                } else prev_sb = -1;
+                prev_b = rest > 0 ? k : -1;
+            }
+            if (prev_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[prev_b & 1], 0));
+            if (prev_sb >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_stripb_[prev_sb & 1], 0));
+            da.rskip = 0; da.slab_lo = 0; da.slab_hi = 0x7fffffff;
+        } else {
+#endif
         int k = 0, last_b = -1;
         for (int P0 = 0; P0 < W; P0 += kPanelW, ++k) {
             da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0;
@@ -333,6 +419,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         }
 #ifndef VBK_EMU
         if (lookahead && last_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[last_b & 1], 0));
+        }
 #endif
     }
     if (da.prof) {
