@@ -435,8 +435,8 @@ def main():
     ap.add_argument("--batch-m", type=int, default=2000)
     ap.add_argument("--batch-n", type=int, default=4000)
     # one host thread per stream runs the LP's symbolic phase (1.2 s per m=2000 LP on one core, measured) and its METHOD
-    # loop; the GPU part of such an LP is 0.2-0.4 s, so the batch is bound by host cores: default = cores / ranks
-    ap.add_argument("--streams", type=int, default=0, help="batch workload: solver streams in flight per GPU (default: host cores / ranks, 2..16)")
+    # loop; the GPU part of such an LP is 0.2-0.4 s, so the batch is bound by host cores (measured: 4 streams 3.5-7.9 LP/s depending on the box, 8 streams 7.7, 16 streams 6.1): default = cores / ranks, at most 8
+    ap.add_argument("--streams", type=int, default=0, help="batch workload: solver streams in flight per GPU (default: host cores / ranks, 2..8)")
     ap.add_argument("--grid", type=int, default=100, help="rowblock workload: grid side R")
     ap.add_argument("--commodities", type=int, default=126, help="rowblock workload: K")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -450,7 +450,7 @@ def main():
 
     if a.workload in ("batch", "rowblock"):
         if a.streams <= 0:
-            a.streams = max(2, min(16, (os.cpu_count() or 8) // max(world, 1)))
+            a.streams = max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))
         if a.batch_per_gpu <= 0:
             a.batch_per_gpu = max(8, 2 * a.streams)
         return multi_gpu_workload(a, rank, local_rank, world)
