@@ -434,7 +434,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="batch workload: LPs per GPU per step (default: 2 per solver stream, at least 8)")
     ap.add_argument("--batch-m", type=int, default=2000)
     ap.add_argument("--batch-n", type=int, default=4000)
-    # one host thread per stream runs the LP's symbolic phase (1.2 s per m=2000 LP on one core, measured) and its METHOD
+    # one host thread per stream runs the LP's symbolic phase (0.4 s per m=2000 LP on one core + handle set-up, measured) and its METHOD
     # loop; the GPU part of such an LP is 0.2-0.4 s, so the batch is bound by host cores (measured: 4 streams 3.5-7.9 LP/s depending on the box, 8 streams 7.7, 16 streams 6.1): default = cores / ranks, at most 8
     ap.add_argument("--streams", type=int, default=0, help="batch workload: solver streams in flight per GPU (default: host cores / ranks, 2..8)")
     ap.add_argument("--grid", type=int, default=100, help="rowblock workload: grid side R")
