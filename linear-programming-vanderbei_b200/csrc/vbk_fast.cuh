@@ -327,6 +327,7 @@ struct WindowSolveArgs {
     const double* S;
     const int* kL; const double* L; const int* mark;
     const int* rowptr; const int* rk; const int* rj;     // ascending row lists (for the coupling rows)
+    const int* spend = nullptr;                          // [W] end of the sparse prefix of every window row's list, or null
     double* z;
     int* counters; const unsigned long long* scal_bits; double epssol;
 };
@@ -343,11 +344,19 @@ static __global__ void __launch_bounds__(kSolveThreads) k_window_gather(WindowSo
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int r = a.T + warp; r < a.N; r += nwarps) {
-        double s = 0.0;
-        for (int t = a.rowptr[r] + lane; t < a.rowptr[r + 1]; t += 32) {
-            const int j = a.rj[t];
-            if (j < a.T && a.mark[j]) s = fma(a.L[a.rk[t]], a.z[j], s);
+        // the sparse columns are the leading part of the ascending row list: stop where the window columns begin
+        // (a window row's list holds up to W of those), four entries per lane in flight
+        const int tend = a.spend ? a.spend[r - a.T] : a.rowptr[r + 1];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int t = a.rowptr[r] + lane; t < tend; t += 128) {
+            const int t1 = t + 32, t2 = t + 64, t3 = t + 96;
+            const int j0 = a.rj[t], j1 = t1 < tend ? a.rj[t1] : a.T, j2 = t2 < tend ? a.rj[t2] : a.T, j3 = t3 < tend ? a.rj[t3] : a.T;
+            if (j0 < a.T && a.mark[j0]) s0 = fma(a.L[a.rk[t]], a.z[j0], s0);
+            if (j1 < a.T && a.mark[j1]) s1 = fma(a.L[a.rk[t1]], a.z[j1], s1);
+            if (j2 < a.T && a.mark[j2]) s2 = fma(a.L[a.rk[t2]], a.z[j2], s2);
+            if (j3 < a.T && a.mark[j3]) s3 = fma(a.L[a.rk[t3]], a.z[j3], s3);
         }
+        double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
         if (lane == 0) a.z[r] -= s;

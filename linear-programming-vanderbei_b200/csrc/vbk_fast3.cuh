@@ -319,7 +319,10 @@ bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, dou
             cn[lane] = ar[c + 1];
             if (kRare) cn[32 + lane] = wmr;
             ldl_fence<kRare>();
-            d = cn[c + 1]; nxt = (c + 2 < 32) ? cn[c + 2] : 0.0;
+            if (((c + 1) & 1) == 0) {                                  // pivot and a_{c+2,c+1} in one 16-byte load
+                const double2 v = *reinterpret_cast<const double2*>(cn + c + 1);
+                d = v.x; nxt = v.y;
+            } else { d = cn[c + 1]; nxt = (c + 2 < 32) ? cn[c + 2] : 0.0; }
             if (kRare) magc = cn[32 + c + 1];
             inv = vbk_rcp_fast(d);
             // the rest of column c's update, in the shadow of that reciprocal

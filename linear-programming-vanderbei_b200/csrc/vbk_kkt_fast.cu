@@ -507,7 +507,7 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     const int N = sym_.N, T = sym_.dense_start;
     WindowSolveArgs wa;
     wa.N = N; wa.T = T; wa.ld = N - T; wa.S = Sw_.p; wa.kL = kL_.p; wa.L = L_.p; wa.mark = mark_.p;
-    wa.rowptr = rowptr_.p; wa.rk = rk_asc_.p; wa.rj = rj_asc_.p; wa.z = z_.p;
+    wa.rowptr = rowptr_.p; wa.rk = rk_asc_.p; wa.rj = rj_asc_.p; wa.z = z_.p; wa.spend = sp_end_.p;
     wa.counters = counters_.p; wa.scal_bits = bits_.p; wa.epssol = 1.0e-6;
     fs.nclaim = T;
     fs.fast = 1;
