@@ -125,19 +125,28 @@ static __global__ void __launch_bounds__(kTriV3Threads, 1) k_window_tri3(Tri3Arg
             cp_async_commit();
         }
         double acc = 0.0;
+        // the owner's own right-hand side entries and the other slices' sum are fetched off the critical path: z[grow]
+        // now, the accumulator together with the last block's z (the other slices finished a hand-off ago)
+        double rz = 0.0, rothers = 0.0;
+        if (owner && tid < kTriPW) rz = rok ? a.z[grow] : 0.0;
         for (int qq = sl; qq < pp; qq += kTriSplit) {
             const int q = a.dir ? a.npan - 1 - qq : qq;
+            const bool lastblk = owner && qq + kTriSplit >= pp;
             // this thread's 64 entries of the block S[R_p, C_q]: row `row`, columns half*64 .. +63 (coalesced over rows)
             double b[64];
             const double* src = a.S + (size_t)grow + (size_t)(q * kTriPW + half * 64) * a.ld;
 #pragma unroll
             for (int c = 0; c < 64; ++c) b[c] = (rok && q * kTriPW + half * 64 + c < a.W) ? __ldg(src + (size_t)c * a.ld) : 0.0;
             if (tid == 0) {
+                if (lastblk) while (vbk_ld_volatile(&arrived[p]) < kTriSplit - 1) __nanosleep(20);
                 while (vbk_ld_volatile(&done[q]) == 0) __nanosleep(20);
                 __threadfence();
             }
             __syncthreads();
-            if (tid < kTriPW) zq[tid] = (q * kTriPW + tid < a.W) ? __ldcg(&a.z[q * kTriPW + tid]) : 0.0;
+            if (tid < kTriPW) {
+                zq[tid] = (q * kTriPW + tid < a.W) ? __ldcg(&a.z[q * kTriPW + tid]) : 0.0;
+                if (lastblk) rothers = __ldcg(&a.racc[(size_t)p * kTriPW + tid]);
+            }
             __syncthreads();
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             const double* zz = zq + half * 64;
@@ -159,18 +168,11 @@ static __global__ void __launch_bounds__(kTriV3Threads, 1) k_window_tri3(Tri3Arg
             }
             continue;
         }
-        // owner: wait for the other slices (they finished a hand-off ago), build the right-hand side
-        if (pp > 0) {
-            if (tid == 0) {
-                while (vbk_ld_volatile(&arrived[p]) < kTriSplit - 1) __nanosleep(20);
-                __threadfence();
-            }
-            __syncthreads();
-        }
+        // owner: build the right-hand side (pp > 0: the last block's iteration above has waited for the other slices)
         if (tid < kTriPW) {
-            double r = rok ? a.z[grow] : 0.0;
+            double r = rz;
             r -= part[tid] + part[kTriPW + tid];
-            if (pp > 0) r -= __ldcg(&a.racc[(size_t)p * kTriPW + tid]);
+            r -= rothers;
             if (a.dir && rok && !a.mark[grow]) {                          // backward: the test comes before the product
                 if (fabs(r) > eps) a.counters[C_CONSISTENT] = 0; else r = 0.0;
             }
