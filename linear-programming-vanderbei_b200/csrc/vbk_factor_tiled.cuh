@@ -402,8 +402,17 @@ static __global__ void __launch_bounds__(kSolveThreads) k_bwd_flags(FlagSolveArg
             const int ke = a.kL[i + 1];
             if (a.fast) {
                 // fast mode: the order of the sum is free -- per-lane partial sums, then a shuffle tree
-                double s = 0.0;
-                for (int k = kb + lane; k < ke; k += 32) s = fma(a.L[k], __ldcg(&a.z[a.iL[k]]), s);
+                // four entries per lane in flight: the column's row index -> z loads are two dependent L2 round trips
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                for (int k = kb + lane; k < ke; k += 128) {
+                    const int k1 = k + 32, k2 = k + 64, k3 = k + 96;
+                    const int i0 = a.iL[k], i1 = k1 < ke ? a.iL[k1] : -1, i2 = k2 < ke ? a.iL[k2] : -1, i3 = k3 < ke ? a.iL[k3] : -1;
+                    s0 = fma(a.L[k], __ldcg(&a.z[i0]), s0);
+                    if (i1 >= 0) s1 = fma(a.L[k1], __ldcg(&a.z[i1]), s1);
+                    if (i2 >= 0) s2 = fma(a.L[k2], __ldcg(&a.z[i2]), s2);
+                    if (i3 >= 0) s3 = fma(a.L[k3], __ldcg(&a.z[i3]), s3);
+                }
+                double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
                 beta -= s;
