@@ -28,10 +28,16 @@
 
 namespace vbk {
 
-#ifndef VBK_EMU
+// (compiled for the host thread emulator too -- tests/test_emu.py checks the bit-exactness claim on the CPU -- with
+// smaller CTAs: every emulated thread is an OS thread)
 constexpr int kSpWarps = 4;
+#ifdef VBK_EMU
+constexpr int kSpHeavyThreads = 64;
+constexpr int kSpHeavyBatch = 64;
+#else
 constexpr int kSpHeavyThreads = 512;
 constexpr int kSpHeavyBatch = 512;
+#endif
 
 struct SparseLevelArgs {
     const int* cols; int ncols;        // the columns of this launch (one etree level, light or heavy share)
@@ -233,8 +239,13 @@ static __global__ void __launch_bounds__(kSpHeavyThreads) k_sparse_level_heavy(S
 }
 
 // Schur assembly of one window column per CTA.  S need not be zeroed for the rows >= i of column i (all are written).
+#ifdef VBK_EMU
+constexpr int kSchur2Threads = 64;
+constexpr int kSchur2Batch = 64;
+#else
 constexpr int kSchur2Threads = 256;
 constexpr int kSchur2Batch = 256;
+#endif
 struct Schur2Args {
     int N, T, ld, cap;                 // cap: doubles of shared memory for the column image
     const int* kL; const int* iL; const double* L; const double* diag;
@@ -332,6 +343,5 @@ static __global__ void __launch_bounds__(kSchur2Threads) k_schur_window2(Schur2A
         __syncthreads();
     }
 }
-#endif  // !VBK_EMU
 
 }  // namespace vbk

@@ -75,6 +75,9 @@ void Kkt::prepare_fast()
         const char* es = std::getenv("VBK_SCHUR");
         light_schur_ = es ? (std::string(es) == "light") : (nsc <= 128LL * W);
     }
+    VBK_CUDA(cudaFuncSetAttribute(k_sparse_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_sparse_level_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_schur_window2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
 #ifndef VBK_EMU
     // kernels are `static` in the headers: this translation unit launches its own copy
     VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
@@ -86,9 +89,6 @@ void Kkt::prepare_fast()
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 128>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 64>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64, 64>::kSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_sparse_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
-    VBK_CUDA(cudaFuncSetAttribute(k_sparse_level_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
-    VBK_CUDA(cudaFuncSetAttribute(k_schur_window2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_window_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTinvSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_window_tri3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriV3Smem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
@@ -121,7 +121,6 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     // 1. columns j < T: the strict task kernel (bit-exact for these columns, dependent-pivot rule
     //    included).  k_tiled_reset has already run.
     int launches = 2;
-#ifndef VBK_EMU
     // throughput kernels of vbk_fast6.cuh unless $VBK_SPARSE=strict / $VBK_SCHUR=light|heavy ask for the first generation
     const char* esp = std::getenv("VBK_SPARSE");
     const size_t sp_smem = (size_t)kSpWarps * sp_cap_ * (2 * sizeof(double) + sizeof(int));
@@ -145,14 +144,10 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         if (!ev_sp0_) { VBK_CUDA(cudaEventCreate(&ev_sp0_)); VBK_CUDA(cudaEventCreate(&ev_sp1_)); }
         VBK_CUDA(cudaEventRecord(ev_sp0_, stream_));
     }
-#else
-    const bool sparse_levels = false;
-#endif
     if (sparse_tasks > 0 && !sparse_levels) {
         ta.phase = 0; ta.task_base = 0; ta.ntasks = sparse_tasks;
         VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(sparse_tasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
     }
-#ifndef VBK_EMU
     if (T > 0 && sparse_levels) {
         SparseLevelArgs sl;
         sl.n_ld = sym_.n; sl.T = T; sl.W = W; sl.kL = kL_.p; sl.iL = iL_.p; sl.L = L_.p; sl.diag = diag_.p; sl.mark = mark_.p;
@@ -173,8 +168,6 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             }
         }
     }
-#endif
-#ifndef VBK_EMU
     if (tune_slot >= 0) {
         VBK_CUDA(cudaEventRecord(ev_sp1_, stream_));
         VBK_CUDA(cudaEventSynchronize(ev_sp1_));
@@ -183,11 +176,9 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         sparse_ms_[tune_slot] = ms;
         sparse_tuned_ = tune_slot + 1;
     }
-#endif
     // 2. Schur complement of the sparse columns on the window, written densely; no dependencies.
     //    Entries outside the fill pattern are never written: start from zero.
     VBK_CUDA(cudaMemsetAsync(Sw_.p, 0, sizeof(double) * (size_t)W * W, stream_));
-#ifndef VBK_EMU
     const char* esc = std::getenv("VBK_SCHUR");
     const size_t sc2_smem = sizeof(double) * ((size_t)W + 2 * kSchur2Batch) + sizeof(int) * 2 * kSchur2Batch;
     const bool schur2 = !esc && sc2_smem <= (size_t)smem_optin_;
@@ -196,9 +187,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         sc.N = N; sc.T = T; sc.ld = W; sc.cap = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
         sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.spend = sp_end_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;
         VBK_LAUNCH(k_schur_window2, std::min(W, num_sms_ * 6), kSchur2Threads, sc2_smem, stream_, sc);
-    } else
-#endif
-    if (light_schur_) {
+    } else if (light_schur_) {
         SchurArgs sc;
         sc.N = N; sc.T = T; sc.ld = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
         sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;

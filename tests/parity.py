@@ -156,3 +156,27 @@ def north_star_tolerances(lp, method, x, y, status, log, iter_slack=1):
     dinf = np.linalg.norm(np.maximum(lp.c - A.T @ y, 0.0)), np.linalg.norm(np.maximum(lp.c - A.T @ yr, 0.0))
     assert abs(pinf[0] - pinf[1]) <= 1e-7 * max(1.0, np.linalg.norm(lp.b))
     assert abs(dinf[0] - dinf[1]) <= 1e-7 * max(1.0, np.linalg.norm(lp.c))
+
+
+def check_fast_sparse_columns(vbkkt, lib, oracle, lp, method, it):
+    """Fast mode keeps the reference's arithmetic for the sparse columns j < T: L, diag and mark of those
+    columns equal the oracle's factor bit for bit (level-scheduled kernels of vbk_fast6.cuh, or the task
+    kernel -- whichever the handle runs)."""
+    E, D, *_ = H.capture_step(oracle, lp, method, it)
+    F = H.oracle_factor_for(oracle, lp)
+    K = H.kkt_for(vbkkt, lib, lp, mode=vbkkt.MODE_FAST)
+    try:
+        F.factor(E, D)
+        out = None
+        for _ in range(3):                   # the first two factorisations time the two paths, the third runs the choice
+            K.factor(E, D)
+            L, d, mk = K.get_factor()
+            T = K.dim - K.window
+            nsp = int(K.kAAt[T])
+            assert np.array_equal(L[:nsp], F.L[:nsp])
+            assert np.array_equal(d[:T], F.diag[:T]) and np.array_equal(mk[:T], F.mark[:T])
+            out = dict(T=T, nsp=nsp, ndep=F.ndep)
+        return out
+    finally:
+        F.close()
+        K.close()

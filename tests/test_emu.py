@@ -62,6 +62,21 @@ def test_emu_fast_mode_kkt_step(vbkkt, emu_lib, oracle_lib, monkeypatch, name, i
     P.check_kkt_step_fast(vbkkt, emu_lib, oracle_lib, H.load_fixture(name), "hsd", it)
 
 
+@pytest.mark.parametrize("name,it,env", [("afiro", 26, {"VBK_SPARSE": "level"}),
+                                         ("afiro", 26, {"VBK_SPARSE": "level", "VBK_SPARSE_HEAVY": "0"}),
+                                         ("sc50b", 12, {"VBK_SPARSE": "level", "VBK_SPARSE_HEAVY": "8"}),
+                                         ("israel", 12, {"VBK_SPARSE": "level", "VBK_WINDOW_RHO": "0.5"}),
+                                         ("afiro", 26, {})])
+def test_emu_fast_mode_sparse_columns_bit_exact(vbkkt, emu_lib, oracle_lib, monkeypatch, name, it, env):
+    """The level-scheduled sparse-column kernels of fast mode (warp per light column, CTA per heavy column;
+    VBK_SPARSE_HEAVY moves the boundary) reproduce the reference's sparse columns bit for bit, dependent pivots
+    included (afiro iterate 26); without VBK_SPARSE the handle measures both paths and keeps one."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    info = P.check_fast_sparse_columns(vbkkt, emu_lib, oracle_lib, H.load_fixture(name), "hsd", it)
+    assert info["T"] > 0 and info["nsp"] > 0
+
+
 def test_emu_fast_mode_full_solve(vbkkt, emu_lib):
     assert P.check_full_solve_fast(vbkkt, emu_lib, H.load_fixture("afiro")) == 0
 
