@@ -21,7 +21,7 @@
 
 namespace vbk {
 
-#ifndef VBK_EMU
+// (also compiled for the host thread emulator: tests/test_emu.py runs the fast-mode solves through these kernels)
 constexpr int kTriPW = 128;                    // rows per panel
 constexpr int kTriSplit = 4;                   // column slices per panel row
 constexpr int kTriV3Threads = 256;
@@ -121,8 +121,12 @@ static __global__ void __launch_bounds__(kTriV3Threads, 1) k_window_tri3(Tri3Arg
         if (owner) {
             // this panel's inverted diagonal block, asynchronously: needed only at the very end
             const double* M = a.Tinv + (size_t)p * kTriPW * kTriPW;
+#ifdef VBK_EMU
+            for (int e = tid; e < kTriPW * kTriPW; e += kTriV3Threads) Msh[e] = M[e];
+#else
             for (int e = tid * 2; e < kTriPW * kTriPW; e += kTriV3Threads * 2) cp_async16(Msh + e, M + e, true);
             cp_async_commit();
+#endif
         }
         double acc = 0.0;
         // the owner's own right-hand side entries and the other slices' sum are fetched off the critical path: z[grow]
@@ -178,7 +182,9 @@ static __global__ void __launch_bounds__(kTriV3Threads, 1) k_window_tri3(Tri3Arg
             }
             rsh[tid] = r;
         }
+#ifndef VBK_EMU
         cp_async_wait<0>();
+#endif
         __syncthreads();
         // v = Tinv_pp r : forward uses the strictly lower part (+ unit diagonal), backward the strictly upper part
         {
@@ -210,6 +216,5 @@ static __global__ void __launch_bounds__(kTriV3Threads, 1) k_window_tri3(Tri3Arg
         if (tid == 0) atomicExch(&done[p], 1);
     }
 }
-#endif  // !VBK_EMU
 
 }  // namespace vbk

@@ -25,14 +25,12 @@ void Kkt::prepare_fast()
     panel_buf2_.alloc((size_t)2 * kPanelBuf2Doubles);
 #endif
     tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
-#ifndef VBK_EMU
     {
         const int npan = (W + kTriPW - 1) / kTriPW;
         tinv_.alloc((size_t)npan * kTriPW * kTriPW);
         tri_racc_.alloc((size_t)npan * kTriPW);
         tri3_flags_.alloc((size_t)2 * npan + 1);
     }
-#endif
     {
         // how many sparse-column contributions do the window rows see?  Few => light Schur kernel.
         long long nsc = 0;
@@ -78,6 +76,8 @@ void Kkt::prepare_fast()
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_schur_window2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_window_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTinvSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_window_tri3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriV3Smem));
 #ifndef VBK_EMU
     // kernels are `static` in the headers: this translation unit launches its own copy
     VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
@@ -89,8 +89,6 @@ void Kkt::prepare_fast()
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 128>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 64>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64, 64>::kSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_window_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTinvSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_window_tri3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriV3Smem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_rows_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsMSmem));
@@ -475,11 +473,9 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         VBK_LAUNCH(k_window_mirror, dim3(nt32, nt32), kVecThreads, 32 * 33 * sizeof(double), stream_, W, W, Sw_.p);
         ++launches;
     }
-#ifndef VBK_EMU
     // 4b. inverses of the 128 x 128 diagonal blocks for the triangular sweeps (vbk_fast5.cuh)
     VBK_LAUNCH(k_window_tinv, (W + kTriPW - 1) / kTriPW, kTriPW, kTinvSmem, stream_, W, W, Sw_.p, tinv_.p);
     ++launches;
-#endif
     // 5. back into the packed storage the strict-layout consumers (tests, get_factor) read
     {
         const int gx = std::max(1, std::min((W + kVecThreads - 1) / kVecThreads, 64));
@@ -514,7 +510,6 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     tr.flags = tri_flags_.p; tr.counters = counters_.p; tr.scal_bits = bits_.p; tr.epssol = 1.0e-6;
     const int gtri = std::max(1, std::min(tr.npanels, num_sms_));
     const size_t sm_tri = (size_t)(kTriThreads / 32) * 32 * sizeof(double) + 16;   // + the claim slot
-#ifndef VBK_EMU
     const bool wsolve_v2 = ew && std::string(ew) == "v2";
     Tri3Args t3;
     t3.W = W; t3.ld = W; t3.npan = (W + kTriPW - 1) / kTriPW; t3.S = Sw_.p; t3.Tinv = tinv_.p; t3.z = z_.p + T;
@@ -527,10 +522,6 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
         t3.dir = dir;
         VBK_LAUNCH(k_window_tri3, g3, kTriV3Threads, kTriV3Smem, stream_, t3);
     };
-#else
-    const bool wsolve_v2 = true;
-    auto sweep3 = [&](int) {};
-#endif
     if (wsolve_v1) VBK_LAUNCH(k_window_fwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
     else if (!wsolve_v2) sweep3(0);
     else {

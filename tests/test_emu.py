@@ -51,12 +51,15 @@ def test_emu_first_generation_kernels_still_bit_exact(vbkkt, emu_lib, oracle_lib
 @pytest.mark.parametrize("name,it,env", [("afiro", 5, {}), ("sc50b", 12, {"VBK_PANEL": "3"}),
                                          ("sc105", 15, {"VBK_WINDOW_RHO": "0.1", "VBK_PANEL": "5"}),
                                          ("sc105", 15, {"VBK_WINDOW_RHO": "0.1", "VBK_DENSE": "v2", "VBK_PANEL": "5"}),
-                                         ("israel", 12, {"VBK_WINDOW_RHO": "0.1"})])
+                                         ("israel", 12, {"VBK_WINDOW_RHO": "0.1"}),
+                                         ("israel", 12, {"VBK_WINDOW_RHO": "0.1", "VBK_WSOLVE": "v2", "VBK_SCHUR": "light"})])
 def test_emu_fast_mode_kkt_step(vbkkt, emu_lib, oracle_lib, monkeypatch, name, it, env):
     """Fast mode: sparse part + Schur assembly + blocked dense LDL^T + dense-window sweeps, several
     panels and a padded (rho < 1) window forced on tiny LPs.  israel at rho = 0.1 has a 131-wide window:
     three of the emulated build's 64-column panels (diagonal block with two sub-blocks, rows below,
-    trailing update); VBK_DENSE=v2 keeps the 32-column-panel generation covered."""
+    trailing update) and two of the 128-row panels of the window sweeps (k_window_tri3 with its four column slices and
+    the inverted diagonal blocks of k_window_tinv); VBK_DENSE=v2, VBK_WSOLVE=v2 and VBK_SCHUR=light keep the earlier
+    generations covered."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     P.check_kkt_step_fast(vbkkt, emu_lib, oracle_lib, H.load_fixture(name), "hsd", it)
