@@ -156,7 +156,9 @@ void vbk_set_iteration_limit(int itnlim);
 float vbk_kkt_last_factor_kernel_ms(vbk_kkt *h);
 /* with $VBK_PROF set: SM cycles per phase of the tiled factor kernel since the last call (8 counters:
  * claim+init, wait, stage, scan, scatter, accumulate, pivot, write) */
-void vbk_kkt_phase_profile(vbk_kkt *h, unsigned long long *out8);
+void vbk_kkt_phase_profile(vbk_kkt *h, unsigned long long *out16);
+/* with $VBK_PROF set: per-column event times (ns) of the last strict factorisation, N x 8 values (csrc/vbk_strict_factor.cuh) */
+void vbk_kkt_trace(vbk_kkt *h, long long *out);
 /* roofline yardsticks measured on the spot: FP64 DFMA TFLOP/s and device copy GB/s */
 double vbk_measure_fp64_tflops(int device);
 double vbk_measure_hbm_gbs(int device);

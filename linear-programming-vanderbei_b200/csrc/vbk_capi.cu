@@ -161,7 +161,8 @@ float vbk_kkt_last_factor_kernel_ms(vbk_kkt* h) { return h->impl.last_factor_ker
 double vbk_measure_fp64_tflops(int device) { return measure_fp64_tflops(device); }
 double vbk_measure_hbm_gbs(int device) { return measure_hbm_gbs(device); }
 
-void vbk_kkt_phase_profile(vbk_kkt* h, unsigned long long* out8) { h->impl.read_phase_profile(out8); }
+void vbk_kkt_phase_profile(vbk_kkt* h, unsigned long long* out16) { h->impl.read_phase_profile(out16); }
+void vbk_kkt_trace(vbk_kkt* h, long long* out) { h->impl.read_trace(out); }
 
 void vbk_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x)
 {

@@ -50,3 +50,24 @@ __device__ __forceinline__ int vbk_ld_volatile(const int* p) {
     return *reinterpret_cast<const volatile int*>(p);
 #endif
 }
+
+// gpu-scope acquire load / release publication used by the dataflow hand-offs (cheaper than the
+// sequentially-consistent __threadfence(): no MEMBAR.SC, the acquire itself orders the loads after it)
+__device__ __forceinline__ int vbk_ld_acquire(const int* p) {
+#ifdef VBK_EMU
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+// orders everything that happened before (own writes and, through a preceding CTA barrier, the other
+// threads' writes) ahead of a following flag write
+__device__ __forceinline__ void vbk_fence_release() {
+#ifdef VBK_EMU
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+#else
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}

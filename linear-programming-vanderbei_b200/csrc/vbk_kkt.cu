@@ -2,6 +2,7 @@
 #include "vbk_kkt.h"
 #include "vbk_kernels.cuh"
 #include "vbk_factor_tiled.cuh"
+#include "vbk_strict_factor.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -185,7 +186,7 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
         if (!sym_.winptr.empty()) winptr_.upload(sym_.winptr, stream_); else winptr_.alloc(1);
         col_left_.alloc(N); col_ready_.alloc(N); piv_flag_.alloc(N); piv_keep_.alloc(N); done_.alloc(N);
         piv_val_.alloc(N); task_max_.alloc(std::max(ntasks, 1));
-        if (std::getenv("VBK_PROF")) { prof_.alloc(8); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 64, stream_)); }
+        if (std::getenv("VBK_PROF")) { prof_.alloc(16); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 128, stream_)); }
         temp_cap_ = std::max(max_cnt, 32);
         tile_doubles_ = std::max(8192, temp_cap_);
         tiled_smem_ = sizeof(double) * ((size_t)tile_doubles_ + temp_cap_ + 2 * kTileMaxBatch + kTiledThreads + 2) +
@@ -210,8 +211,79 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
         tiled_grid_ = (int)g2;
         if ((size_t)tiled_grid_ > (size_t)factor_grid_) slotmap_.alloc((size_t)tiled_grid_ * N);
     }
+    // third-generation strict factor kernel: launch geometry
+    {
+        const char* ef = std::getenv("VBK_FACTOR");
+        const int ntasks = sym_.ntasks();
+        int max_cnt = 1;
+        for (int t = 0; t < ntasks; ++t) max_cnt = std::max(max_cnt, sym_.task_cnt[t]);
+        pipe_cap_ = max_cnt <= 32 ? 32 : (max_cnt <= 64 ? 64 : 128);
+        use_pipe_ = use_tiled_ && !(ef && std::strcmp(ef, "tiled") == 0) && max_cnt <= 32 * kPipeMaxChains;
+        pipe_warps_ = kPipeWarpsDefault;
+#ifndef VBK_EMU
+        if (const char* e = std::getenv("VBK_PIPE_WARPS")) pipe_warps_ = std::max(3, std::min(kPipeWarpsDefault, std::atoi(e)));
+#endif
+        pipe_stages_ = kPipeStagesMax;
+        if (const char* e = std::getenv("VBK_PIPE_STAGES")) pipe_stages_ = std::max(2, std::min(16, std::atoi(e)));
+        while (pipe_stages_ > 2 && pipe_smem_bytes(pipe_cap_, pipe_stages_, sym_.rowblk, pipe_warps_) > (size_t)smem_optin_) --pipe_stages_;
+        pipe_smem_ = pipe_smem_bytes(pipe_cap_, pipe_stages_, sym_.rowblk, pipe_warps_);
+        if (pipe_smem_ > (size_t)smem_optin_) use_pipe_ = false;
+        if (use_pipe_) {
+            col_pub_.alloc(N); col_done_.alloc(N);
+            int occ3 = 1;
+#ifndef VBK_EMU
+            VBK_CUDA(cudaFuncSetAttribute(k_factor_pipe<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+            VBK_CUDA(cudaFuncSetAttribute(k_factor_pipe<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+            VBK_CUDA(cudaFuncSetAttribute(k_factor_pipe<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+            VBK_CUDA(cudaFuncSetAttribute(k_factor_pipe<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+            VBK_CUDA(cudaFuncSetAttribute(k_factor_pipe<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+            VBK_CUDA(cudaFuncSetAttribute(k_factor_pipe<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+#endif
+            if (pipe_cap_ == 32) VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, (k_factor_pipe<1, false>), pipe_warps_ * 32, pipe_smem_));
+            else if (pipe_cap_ == 64) VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, (k_factor_pipe<2, false>), pipe_warps_ * 32, pipe_smem_));
+            else VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, (k_factor_pipe<4, false>), pipe_warps_ * 32, pipe_smem_));
+            occ3 = std::max(1, occ3);
+            if (const char* e = std::getenv("VBK_PIPE_OCC")) occ3 = std::max(1, std::min(occ3, std::atoi(e)));
+            pipe_grid_ = (int)std::max<long long>(1, std::min<long long>((long long)num_sms_ * occ3, ntasks));
+#ifdef VBK_EMU
+            pipe_grid_ = std::max(1, std::min(3, ntasks));
+#endif
+        }
+    }
     if (mode_ == kFast) prepare_fast();
     VBK_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Kkt::launch_factor_pipe()
+{
+    const int N = sym_.N;
+    PipeArgs pa;
+    pa.N = N; pa.n_ld = sym_.n; pa.ntasks = sym_.ntasks(); pa.nstages = pipe_stages_;
+    pa.kL = kL_.p; pa.iL = iL_.p; pa.L = L_.p; pa.diag = diag_.p; pa.mark = mark_.p;
+    pa.rowptr = rowptr_.p; pa.rk = rk_sig_.p; pa.rj = rj_sig_.p; pa.perm = perm_.p;
+    pa.task_col = task_col_.p; pa.task_blk = task_blk_.p; pa.task_pos0 = task_pos0_.p; pa.task_cnt = task_cnt_.p;
+    pa.col_task0 = col_task0_.p; pa.col_ntask = col_ntask_.p;
+    pa.winptr = winptr_.p; pa.nblk = sym_.nblk; pa.rowblk = sym_.rowblk; pa.slice_row0 = sym_.slice_row0;
+    pa.col_pub = col_pub_.p; pa.col_done = col_done_.p; pa.task_max = task_max_.p;
+    pa.counters = counters_.p; pa.scal_bits = bits_.p; pa.epsnum = 0.0;        // _EPSNUM, ldlt.c:29
+    if (std::getenv("VBK_PROF") && !prof_.p) { prof_.alloc(16); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 128, stream_)); }
+    pa.prof = prof_.p;
+    if (pa.prof && !trace_.p) trace_.alloc((size_t)N * 8);
+    pa.trace = trace_.p;
+    if (debug_) std::fprintf(stderr, "vbk factor: pipe kernel, grid %d, %d warps, %d stages, cap %d, smem %zu, %d tasks\n",
+                             pipe_grid_, pipe_warps_, pipe_stages_, pipe_cap_, pipe_smem_, pa.ntasks);
+    VBK_LAUNCH(k_pipe_reset, vec_grid(N), kVecThreads, 0, stream_, N, col_pub_.p, col_done_.p, counters_.p);
+    VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
+    if (pa.prof) {
+        if (pipe_cap_ == 32) VBK_LAUNCH((k_factor_pipe<1, true>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else if (pipe_cap_ == 64) VBK_LAUNCH((k_factor_pipe<2, true>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else VBK_LAUNCH((k_factor_pipe<4, true>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+    } else {
+        if (pipe_cap_ == 32) VBK_LAUNCH((k_factor_pipe<1, false>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else if (pipe_cap_ == 64) VBK_LAUNCH((k_factor_pipe<2, false>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else VBK_LAUNCH((k_factor_pipe<4, false>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+    }
+    VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
 }
 
 void Kkt::read_scalars()
@@ -219,6 +291,13 @@ void Kkt::read_scalars()
     bits_.download(pin_bits_, S_COUNT, stream_);
     scal_.download(pin_scal_, S_COUNT, stream_);
     counters_.download(pin_cnt_, C_COUNT, stream_);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Kkt::read_trace(long long* out)
+{
+    if (!trace_.p) return;
+    trace_.download(out, (size_t)sym_.N * 8, stream_);
     VBK_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -231,13 +310,13 @@ float Kkt::last_factor_kernel_ms()
     return ms;
 }
 
-void Kkt::read_phase_profile(unsigned long long out[8])
+void Kkt::read_phase_profile(unsigned long long out[16])
 {
-    for (int u = 0; u < 8; ++u) out[u] = 0;
+    for (int u = 0; u < 16; ++u) out[u] = 0;
     if (!prof_.p) return;
-    prof_.download(out, 8, stream_);
+    prof_.download(out, 16, stream_);
     VBK_CUDA(cudaStreamSynchronize(stream_));
-    VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 64, stream_));
+    VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 128, stream_));
 }
 
 double Kkt::epsdiag() { require_device("epsdiag"); read_scalars(); return pin_scal_[S_EPSDIAG]; }
@@ -267,6 +346,15 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
     VBK_CUDA(cudaMemsetAsync(L_.p, 0, sizeof(double) * (size_t)lnz, stream_));
     VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapA_.p, A_val_.p, L_.p);
     VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapAt_.p, At_val_.p, L_.p);
+    if (use_pipe_ && !(mode_ == kFast && sym_.dense_start < N && fast_ready_)) {
+        // K2/K4 numeric LDL^T, pipelined slice tasks (vbk_strict_factor.cuh)
+        launch_factor_pipe();
+        VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);
+        VBK_LAUNCH(k_update_epsdiag, 1, 32, 0, stream_, scal_.p, bits_.p);
+        VBK_CHECK_LAUNCH();
+        stats.kernel_launches += 9;
+        return;
+    }
     if (use_tiled_) {
         // K2/K4 numeric LDL^T, batched-tile / sliced-column kernel (vbk_factor_tiled.cuh)
         VBK_LAUNCH(k_tiled_reset, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, col_ntask_.p, pend_.p,

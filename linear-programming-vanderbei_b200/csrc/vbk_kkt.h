@@ -13,6 +13,7 @@ namespace vbk {
 
 enum Mode { kStrict = 0, kFast = 1 };
 struct TiledArgs;
+struct PipeArgs;
 struct FlagSolveArgs;
 struct SolveArgs;
 
@@ -90,7 +91,9 @@ public:
     float last_factor_kernel_ms();
     // $VBK_PROF=1: cycles spent per phase by thread 0 of every CTA of the tiled factor kernel since the
     // last call (8 counters, see vbk_factor_tiled.cuh); zeros when profiling is off
-    void read_phase_profile(unsigned long long out[8]);
+    void read_phase_profile(unsigned long long out[16]);
+    // $VBK_PROF: per-column event times of the last strict factorisation, [N][8] (vbk_strict_factor.cuh)
+    void read_trace(long long* out);
 
     int num_sms() const { return num_sms_; }
     int vec_grid(long long n) const;
@@ -135,10 +138,17 @@ private:
     DevArray<int> task_col_, task_blk_, task_pos0_, task_cnt_, col_task0_, col_ntask_, winptr_;
     DevArray<int> col_left_, col_ready_, piv_flag_, piv_keep_, done_;
     DevArray<double> piv_val_, task_max_;
+    DevArray<long long> trace_;
     DevArray<unsigned long long> prof_;   // $VBK_PROF: per-phase cycle counters of the tiled factor kernel
     int tiled_grid_ = 1, tile_doubles_ = 8192, temp_cap_ = 512;
     size_t tiled_smem_ = 0;
     void fill_tiled_args(TiledArgs& ta);
+    // third-generation strict factor kernel (vbk_strict_factor.cuh): producer/consumer pipeline per slice task
+    bool use_pipe_ = true;
+    DevArray<int> col_pub_, col_done_;
+    int pipe_grid_ = 1, pipe_warps_ = 8, pipe_stages_ = 8, pipe_cap_ = 32;
+    size_t pipe_smem_ = 0;
+    void launch_factor_pipe();
 
     // fast mode (vbk_fast.cuh, vbk_kkt_fast.cu): dense scratch for the trailing window
     bool fast_ready_ = false, light_schur_ = false;

@@ -1,0 +1,443 @@
+// vbk_strict_factor.cuh -- STRICT numeric LDL^T (lltnum, reference src/ipo/ldlt.c:565-631), third
+// generation: the same bits as the reference, organised around the only thing that bounds strict
+// mode -- the dependent chain of rounded additions.
+//
+// Column i of the reference accumulates, for every row below it,
+//     temp[row] = (((0 + p_1) + p_2) + ...),   p_q = (L[i,j_q] * d_jq) * L[row,j_q]      (ldlt.c:572,583,588)
+// over its contributing columns j_q in link-list order sigma_i.  The products
+// are independently rounded, so they can be formed by anybody at any time; only the additions are a
+// chain, one chain per entry of the column, |sigma_i| links long.  sigma_i starts with the column that
+// finished LAST (in the dense tail sigma_i = [i-1, i-3, ..., i-4, i-2]), so a column's chains cannot
+// start before its predecessor is final: per factorisation the critical path is ~Lnz dependent FP64
+// additions (dfl001: 6.96 M of 7.16 M), 8 cycles each on B200.  The second-generation kernel
+// (vbk_factor_tiled.cuh) spent ~150 cycles per link: load, scatter, barrier, add phases of a whole CTA
+// in sequence, all of it starting only when the last child had finished.  Here a CTA is a pipeline:
+//
+//   producer warps   form the products of 32 contributors at a time into a ring of shared-memory
+//                    tiles tile[stage][q][slot] -- row q holds contributor q's products for every row
+//                    of the task, +0.0 where the contributor has no entry (adding +0.0 is exact and the
+//                    accumulator is never -0.0).  They wait per CONTRIBUTOR for its column to be final
+//                    (col_done[j]), so everything except the products of the last child is staged
+//                    before that child finishes;
+//   consumer warp    one lane per row of the task (up to 4 rows per lane when row blocks are wider
+//                    than 32): the accumulator lives in a register, a ring stage is 32 back-to-back
+//                    dependent additions per lane, in the reference's order;
+//   pivot warp       (pivot-owning slice only) the diagonal's own chain diagi -= lij*(lij*dj)
+//                    (ldlt.c:573) from the staged (lij, lij*dj) pairs.
+//
+// Tasks are (column, 32-row block) slices as before (vbk_symbolic.h), claimed in index order by
+// persistent CTAs.  The LAST slice of a column owns the pivot: the other slices publish their
+// undivided entries and leave at once (no CTA ever waits for a task claimed after its own, so the
+// kernel cannot deadlock whatever the grid or however many handles share the GPU); the owner applies
+// the pivot rule (ldlt.c:600-614, max|offdiag| over all slices only when the pivot is exactly 0),
+// divides the whole column and raises col_done[i].
+#pragma once
+#include "vbk_kernels.cuh"
+
+namespace vbk {
+
+constexpr int kPipeQ = 32;            // contributors per ring stage
+constexpr int kPipeMaxChains = 4;     // rows per consumer lane: tasks of up to 128 rows
+#ifdef VBK_EMU
+constexpr int kPipeWarpsDefault = 4;  // consumer, pivot, 2 producers (every CUDA thread is an OS thread there)
+constexpr int kPipeStagesMax = 3;
+#else
+constexpr int kPipeWarpsDefault = 16; // consumer, pivot, 14 producers
+constexpr int kPipeStagesMax = 16;
+#endif
+
+struct PipeArgs {
+    int N, n_ld, ntasks;
+    int nstages;        // ring depth
+    const int* kL; const int* iL; double* L; double* diag; int* mark;
+    const int* rowptr; const int* rk; const int* rj;      // row lists in sigma order
+    const int* perm;
+    const int* task_col; const int* task_blk; const int* task_pos0; const int* task_cnt;
+    const int* col_task0; const int* col_ntask;
+    const int* winptr; int nblk, rowblk, slice_row0;
+    int* col_pub;       // [N] non-owner slices of the column that have published their undivided entries
+    int* col_done;      // [N] 1 once L[:,j], diag[j] and mark[j] are final
+    double* task_max;   // [ntasks] max|undivided entry| of a non-owner slice
+    int* counters; const unsigned long long* scal_bits; double epsnum;
+    // optional [16] cycle counters ($VBK_PROF), lane 0 of each role: 0 consumer waits for a stage, 1 consumer adds,
+    // 2 producer waits for a free slot, 3 static structure + zero fill, 4 waits for the contributors' columns,
+    // 5 fence + lij, dj, 6 products, 7 publish; 8 claim + task setup, 9 epilogue up to col_pub / pivot wait,
+    // 10 owner waits for the other slices, 11 pivot rule, 12 divide, 13 fence + col_done, 14 groups staged, 15 tasks
+    unsigned long long* prof;
+    // optional [N][8] per-column event times in ns (globaltimer), written by the pivot-owning slice ($VBK_PROF):
+    // 0 claim, 1 first ring stage consumed, 2 chains finished, 3 all slices published, 4 col_done raised,
+    // 5 contributor groups, 6 slices, 7 SM
+    long long* trace;
+};
+
+// what a producer stages per contributor besides the products: lij*dj, the first entry of column j in the rows of the
+// task and how many there are (16 bytes: one broadcast LDS.128 per use)
+struct alignas(16) PipeMeta { double w; int kb; int len; };
+
+// bytes of dynamic shared memory the kernel needs
+inline size_t pipe_smem_bytes(int cap, int nstages, int rowblk, int nwarps)
+{
+    size_t d = (size_t)nstages * kPipeQ * cap      // product tiles
+             + (size_t)2 * nstages * kPipeQ        // PipeMeta per staged contributor
+             + (size_t)nstages * kPipeQ            // lij per staged contributor
+             + (size_t)cap + nwarps + 2;           // undivided column, per-warp max, pivot
+    size_t i = (size_t)nstages + 2 + cap + rowblk + 8;
+    return d * sizeof(double) + i * sizeof(int);
+}
+
+__device__ __forceinline__ long long vbk_globaltimer() {
+#ifdef VBK_EMU
+    return 0;
+#else
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+__device__ __forceinline__ void vbk_pause() {
+#ifdef VBK_EMU
+    sched_yield();
+#endif
+}
+__device__ __forceinline__ void vbk_st_volatile(int* p, int v) {
+#ifdef VBK_EMU
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+    *reinterpret_cast<volatile int*>(p) = v;
+#endif
+}
+
+static __global__ void k_pipe_reset(int N, int* __restrict__ col_pub, int* __restrict__ col_done, int* __restrict__ counters)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) { col_pub[t] = 0; col_done[t] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[C_NEXT] = 0; counters[C_NDEP] = 0; }
+}
+
+// Products of one ring stage.  Written without data-dependent branches: inactive lanes skip their loads by
+// predication, so the loads of a whole batch of contributors are in flight together; the slot of an entry comes from
+// the block's row -> slot map (BLK) or from a branch-free binary search over the task's sorted rows (whole columns).
+template <int NCH, bool BLK>
+__device__ __forceinline__ void pipe_products(const PipeArgs& a, const PipeMeta* __restrict__ mp, double* __restrict__ tp,
+                                              const int* __restrict__ blockmap, const int* __restrict__ rows,
+                                              int cnt, int bs, int lane)
+{
+    constexpr int cap = 32 * NCH;
+    constexpr int QB = 16 / NCH;                                   // contributors whose loads are in flight together
+    constexpr int kSteps = (NCH == 1) ? 5 : (NCH == 2 ? 6 : 7);    // log2(cap)
+    for (int q0 = 0; q0 < kPipeQ; q0 += QB) {
+        int ri[QB][NCH];
+        double val[QB][NCH];
+#pragma unroll
+        for (int u = 0; u < QB; ++u) {
+            const PipeMeta m = mp[q0 + u];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int e = lane + 32 * c;
+                val[u][c] = 0.0;
+                ri[u][c] = bs;
+                if (e < m.len) { val[u][c] = __ldcg(&a.L[m.kb + e]); ri[u][c] = a.iL[m.kb + e]; }
+                if (m.len != cnt) tp[(q0 + u) * cap + e] = 0.0;    // +0.0 where the contributor has no entry
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < QB; ++u) {
+            const PipeMeta m = mp[q0 + u];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int e = lane + 32 * c;
+                int slot;
+                if (BLK) slot = blockmap[ri[u][c] - bs];
+                else {
+                    slot = 0;                // rows[] is sorted and holds the row: largest s with rows[s] <= row
+#pragma unroll
+                    for (int b2 = kSteps - 1; b2 >= 0; --b2) slot += (rows[slot + (1 << b2)] <= ri[u][c]) ? (1 << b2) : 0;
+                }
+                if (e < m.len) tp[(q0 + u) * cap + slot] = m.w * val[u][c];                // lij_dj*AAt[kk], ldlt.c:583
+            }
+        }
+    }
+}
+
+template <int NCH, bool PROF>
+static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(PipeArgs a)
+{
+    VBK_DYN_SMEM(raw);
+    constexpr int cap = 32 * NCH;
+    const int S = a.nstages;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int P = nwarps - 2;                                   // producer warps
+    double* tile = reinterpret_cast<double*>(raw);              // [S][kPipeQ][cap]
+    PipeMeta* s_meta = reinterpret_cast<PipeMeta*>(tile + (size_t)S * kPipeQ * cap);   // [S][kPipeQ]
+    double* s_l = reinterpret_cast<double*>(s_meta + S * kPipeQ);                       // [S][kPipeQ]
+    double* temp = s_l + S * kPipeQ;                            // [cap] undivided entries of the task
+    double* s_red = temp + cap;                                 // [nwarps]
+    double* s_dbl = s_red + nwarps;                             // [0] pivot, [1] diagonal chain result
+    int* full = reinterpret_cast<int*>(s_dbl + 2);              // [S] group number + 1 staged in the slot
+    int* cons = full + S;                                       // [0] groups consumed by the rows, [1] by the pivot chain
+    int* rows = cons + 2;                                       // [cap] row indices of the task, padded with INT_MAX
+    int* blockmap = rows + cap;                                 // [rowblk] row-in-block -> slot
+    int* s_ctl = blockmap + a.rowblk;                           // [0] task, [1] keep
+
+    const double thresh = a.epsnum * bits_to_double(a.scal_bits[S_MAXDIAG]);     // ldlt.c:600
+    const int wstride = a.nblk + 1;
+    long long pacc[PROF ? 16 : 1];
+#pragma unroll
+    for (int u = 0; u < (PROF ? 16 : 1); ++u) pacc[u] = 0;
+    long long tlast = PROF ? vbk_clock() : 0;
+    const bool profiling = PROF && a.prof != nullptr && lane == 0;
+#define VBK_PTICK(slot) do { if (PROF && profiling) { const long long now_ = vbk_clock(); pacc[PROF ? slot : 0] += now_ - tlast; tlast = now_; } } while (0)
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ctl[0] = atomicAdd(&a.counters[C_NEXT], 1);
+        __syncthreads();
+        const int t = s_ctl[0];
+        if (t >= a.ntasks) break;
+        const int i = a.task_col[t], blk = a.task_blk[t], p0 = a.task_pos0[t], cnt = a.task_cnt[t];
+        const int nslices = a.col_ntask[i];
+        const bool owner = (t == a.col_task0[i] + nslices - 1);
+        const int bs = a.slice_row0 + (blk < 0 ? 0 : blk) * a.rowblk;             // first row of the block
+        const int rb = a.rowptr[i], re = a.rowptr[i + 1];
+        const int ngroups = (re - rb + kPipeQ - 1) / kPipeQ;
+
+        if (blk >= 0) for (int s = tid; s < a.rowblk; s += nt) blockmap[s] = 0;
+        __syncthreads();
+        for (int s = tid; s < cap; s += nt) {
+            int row = 0x7fffffff;
+            if (s < cnt) { row = a.iL[p0 + s]; if (blk >= 0) blockmap[row - bs] = s; }
+            rows[s] = row;
+        }
+        if (tid < S) full[tid] = 0;
+        if (tid < 2) cons[tid] = 0;
+        __syncthreads();
+        VBK_PTICK(8);
+        if (PROF && profiling && tid == 0) pacc[PROF ? 15 : 0] += 1;
+        const bool tracing = PROF && a.trace != nullptr && owner && lane == 0;
+        if (tracing && tid == 0) {
+            long long* tr = a.trace + (size_t)i * 8;
+            tr[0] = vbk_globaltimer(); tr[1] = tr[0]; tr[2] = tr[0]; tr[5] = ngroups; tr[6] = nslices;
+#ifndef VBK_EMU
+            unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[7] = smid;
+#endif
+        }
+
+        double acc[NCH];
+        double kval[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { acc[c] = 0.0; kval[c] = 0.0; }
+        double diagi = 0.0;
+
+        if (warp == 0) {
+            // ---- consumer: one register accumulator per row, the reference's additions in the reference's order
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) if (lane + 32 * c < cnt) kval[c] = __ldcg(&a.L[p0 + lane + 32 * c]);
+            for (int g = 0; g < ngroups; ++g) {
+                const int st = g % S;
+                while (vbk_ld_volatile(&full[st]) != g + 1) vbk_pause();
+                __threadfence_block();
+                VBK_PTICK(0);
+                if (tracing && g == 0) a.trace[(size_t)i * 8 + 1] = vbk_globaltimer();
+                const double* tp = tile + (size_t)st * kPipeQ * cap + lane;
+#pragma unroll
+                for (int q = 0; q < kPipeQ; ++q) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) acc[c] += tp[q * cap + 32 * c];          // temp[row] += lij_dj*AAt[kk]
+                }
+                __syncwarp();
+                if (lane == 0) vbk_st_volatile(&cons[0], g + 1);
+                VBK_PTICK(1);
+            }
+        } else if (warp == 1) {
+            // ---- pivot chain (owner slice only): diagi -= lij*lij_dj in the same order (ldlt.c:573)
+            if (owner) {
+                diagi = __ldcg(&a.diag[i]);
+                for (int g = 0; g < ngroups; ++g) {
+                    const int st = g % S;
+                    while (vbk_ld_volatile(&full[st]) != g + 1) vbk_pause();
+                    __threadfence_block();
+                    const double* pl = s_l + st * kPipeQ;
+                    const PipeMeta* pm = s_meta + st * kPipeQ;
+#pragma unroll
+                    for (int q = 0; q < kPipeQ; ++q) { const double p = pl[q] * pm[q].w; diagi -= p; }
+                    __syncwarp();
+                    if (lane == 0) vbk_st_volatile(&cons[1], g + 1);
+                }
+            }
+        } else {
+            // ---- producers: stage the products of 32 contributors per ring slot.  Software pipeline over the warp's
+            // groups: the static structure of the NEXT group (row-list entries, column end, block range) is fetched
+            // while the products of the current one are formed, and so are its readiness flag and lij, dj when the
+            // contributing columns are already final -- in steady state only the product loads are exposed.
+            const int pw = warp - 2;
+            int k = 0, j = 0, kb = 0, len = 0, flag = 1;
+            bool valid = false;
+            double lij = 0.0, dj = 0.0;
+            if (pw < ngroups) {
+                const int tq = rb + pw * kPipeQ + lane;
+                valid = tq < re;
+                if (valid) {
+                    k = a.rk[tq]; j = a.rj[tq];
+                    kb = k + 1;
+                    int ke = a.kL[j + 1];
+                    if (blk >= 0) {
+                        const int* wp = a.winptr + (size_t)j * wstride;
+                        const int lo = wp[blk], hi = wp[blk + 1];
+                        if (lo > kb) kb = lo;
+                        if (hi < ke) ke = hi;
+                    }
+                    len = ke > kb ? ke - kb : 0;       // entries of column j in the rows of this task
+                    flag = vbk_ld_acquire(&a.col_done[j]);
+                    if (flag) { lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]); }
+                }
+            }
+            for (int g = pw; g < ngroups; g += P) {
+                const int st = g % S;
+                double* tp = tile + (size_t)st * kPipeQ * cap;
+                // (1) row-list entries of the warp's next group
+                const int gn = g + P;
+                const int tqn = rb + gn * kPipeQ + lane;
+                const bool nvalid = gn < ngroups && tqn < re;
+                int nk = 0, nj = 0;
+                if (nvalid) { nk = a.rk[tqn]; nj = a.rj[tqn]; }
+                VBK_PTICK(3);
+                // (2) a free ring slot
+                if (g >= S) {
+                    const int need = g - S + 1;
+                    while (vbk_ld_volatile(&cons[0]) < need || (owner && vbk_ld_volatile(&cons[1]) < need)) vbk_pause();
+                    __threadfence_block();
+                }
+                VBK_PTICK(2);
+                // (3) the contributor's column must be final (acquire: the loads below see its final values)
+                if (valid && !flag) {
+                    while (vbk_ld_acquire(&a.col_done[j]) == 0) { __nanosleep(20); vbk_pause(); }
+                    lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]);
+                }
+                VBK_PTICK(4);
+                {
+                    PipeMeta m;
+                    m.w = lij * dj;                                    // lij_dj, ldlt.c:572
+                    m.kb = kb; m.len = len;
+                    s_meta[st * kPipeQ + lane] = m;
+                    s_l[st * kPipeQ + lane] = lij;
+                }
+                // (4) column end and block range of the next group's contributors
+                int nke = 0, nlo = 0, nhi = 0x7fffffff;
+                if (nvalid) {
+                    nke = a.kL[nj + 1];
+                    if (blk >= 0) { const int* wp = a.winptr + (size_t)nj * wstride; nlo = wp[blk]; nhi = wp[blk + 1]; }
+                }
+                __syncwarp();
+                VBK_PTICK(5);
+                // (5) products
+                if (blk >= 0) pipe_products<NCH, true>(a, s_meta + st * kPipeQ, tp, blockmap, rows, cnt, bs, lane);
+                else          pipe_products<NCH, false>(a, s_meta + st * kPipeQ, tp, blockmap, rows, cnt, bs, lane);
+                VBK_PTICK(6);
+                // (6) next group: entry range, readiness, lij and dj if the column is final already
+                int nkb = nk + 1, nlen = 0, nflag = 1;
+                double nlij = 0.0, ndj = 0.0;
+                if (nvalid) {
+                    if (nlo > nkb) nkb = nlo;
+                    if (nhi < nke) nke = nhi;
+                    nlen = nke > nkb ? nke - nkb : 0;
+                    nflag = vbk_ld_acquire(&a.col_done[nj]);
+                    if (nflag) { nlij = __ldcg(&a.L[nk]); ndj = __ldcg(&a.diag[nj]); }
+                }
+                // (7) publish the stage
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) vbk_st_volatile(&full[st], g + 1);
+                VBK_PTICK(7);
+                if (PROF && profiling) pacc[PROF ? 14 : 0] += 1;
+                k = nk; j = nj; kb = nkb; len = nlen; valid = nvalid; flag = nflag; lij = nlij; dj = ndj;
+            }
+        }
+
+        // ---- column entries minus the accumulated updates (ldlt.c:596-599), max|.| of the slice
+        if (warp == 0) {
+            if (tracing && ngroups > 0) a.trace[(size_t)i * 8 + 2] = vbk_globaltimer();
+            double mymax = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int s = lane + 32 * c;
+                if (s < cnt) {
+                    const double v = kval[c] - acc[c];
+                    temp[s] = v;
+                    if (!owner) a.L[p0 + s] = v;
+                    const double av = fabs(v);
+                    if (av > mymax) mymax = av;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mymax, d); if (o > mymax) mymax = o; }
+            if (lane == 0) {
+                s_red[0] = mymax;
+                if (!owner) a.task_max[t] = mymax;
+            }
+
+        } else if (warp == 1 && owner && lane == 0) {
+            s_dbl[1] = diagi;
+        }
+        __syncthreads();
+        if (PROF && profiling) tlast = vbk_clock();         // roles that idled at the barrier do not count it
+        if (!owner) {
+            // undivided entries + slice maximum were written before the barrier: release, then raise col_pub
+            if (tid == 0) { vbk_fence_release(); atomicAdd(&a.col_pub[i], 1); }
+            VBK_PTICK(9);
+            continue;
+        }
+        VBK_PTICK(9);
+        if (tid == 0) {
+            if (nslices > 1) {
+                while (vbk_ld_acquire(&a.col_pub[i]) != nslices - 1) vbk_pause();
+            }
+            VBK_PTICK(10);
+            if (tracing) a.trace[(size_t)i * 8 + 3] = vbk_globaltimer();
+            double piv = s_dbl[1];
+            int keep = 1;
+            if (fabs(piv) <= thresh) {                                  // dependent pivot, ldlt.c:600-614
+                double colmax = s_red[0];
+                const int tb = a.col_task0[i];
+                for (int u = 0; u + 1 < nslices; ++u) { const double m = __ldcg(&a.task_max[tb + u]); if (m > colmax) colmax = m; }
+                atomicAdd(&a.counters[C_NDEP], 1);
+                if (colmax < 1.0e+6 * 1.0e-8) keep = 0;
+                else piv = (a.perm[i] < a.n_ld ? -1 : 1) * 1.0e-8;
+            }
+            a.diag[i] = piv;
+            if (!keep) a.mark[i] = 0;
+            s_dbl[0] = piv;
+            s_ctl[1] = keep;
+            VBK_PTICK(11);
+        }
+        __syncthreads();
+        if (PROF && profiling) tlast = vbk_clock();
+        {
+            const double piv = s_dbl[0];
+            const int keep = s_ctl[1];
+            for (int s = tid; s < cnt; s += nt) a.L[p0 + s] = keep ? temp[s] / piv : 0.0;         // ldlt.c:621-627
+            // the other slices' rows: four independent loads in flight per thread
+            for (int p = a.kL[i] + tid; p < p0; p += 4 * nt) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (p + u * nt < p0) ? __ldcg(&a.L[p + u * nt]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (p + u * nt < p0) a.L[p + u * nt] = keep ? v[u] / piv : 0.0;
+            }
+        }
+        VBK_PTICK(12);
+        __syncthreads();
+        if (tid == 0) { vbk_fence_release(); atomicExch(&a.col_done[i], 1); if (tracing) a.trace[(size_t)i * 8 + 4] = vbk_globaltimer(); }
+        VBK_PTICK(13);
+    }
+    if (PROF && profiling) {
+        // counters 0-1 come from warp 0, 2-7 and 14 from the producers, 8-13 and 15 from thread 0 (warp 0): no double counting
+        if (warp == 0) { for (int u = 0; u < 2; ++u) atomicAdd(&a.prof[u], (unsigned long long)pacc[u]);
+                         for (int u = 8; u < 14; ++u) atomicAdd(&a.prof[u], (unsigned long long)pacc[u]);
+                         atomicAdd(&a.prof[15], (unsigned long long)pacc[15]); }
+        else if (warp >= 2) { for (int u = 2; u < 8; ++u) atomicAdd(&a.prof[u], (unsigned long long)pacc[u]);
+                              atomicAdd(&a.prof[14], (unsigned long long)pacc[14]); }
+    }
+#undef VBK_PTICK
+}
+
+}  // namespace vbk

@@ -297,7 +297,7 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
     }
 
     // task decomposition for the numeric kernels (see vbk_symbolic.h)
-    if (const char* e = std::getenv("VBK_WHOLE_CAP")) whole_cap = std::max(1, std::atoi(e)); else whole_cap = 64;
+    if (const char* e = std::getenv("VBK_WHOLE_CAP")) whole_cap = std::max(1, std::atoi(e)); else whole_cap = 32;
     slice_row0 = N;
     for (int j = 0; j < N; ++j)
         if (kL[j + 1] - kL[j] > whole_cap) { slice_row0 = j; break; }
@@ -339,6 +339,31 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
             }
         }
         col_ntask[j] = (int)task_col.size() - col_task0[j];
+    }
+
+    if (std::getenv("VBK_SYM_STATS")) {
+        // how much of the factorisation's work lies in contributor segments that cover every row of their task
+        long long full_pairs = 0, part_pairs = 0, empty_pairs = 0, full_prod = 0, part_prod = 0, run_prod = 0;
+        for (int t = 0; t < (int)task_col.size(); ++t) {
+            const int i = task_col[t], blk = task_blk[t], c = task_cnt[t];
+            for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+                const int j = rj_sig[q];
+                int kb = rk_sig[q] + 1, ke = kL[j + 1];
+                if (blk >= 0) {
+                    const int* wp = &winptr[(size_t)j * (nblk + 1)];
+                    kb = std::max(kb, wp[blk]); ke = std::min(ke, wp[blk + 1]);
+                }
+                const int len = std::max(0, ke - kb);
+                if (len == 0) ++empty_pairs;
+                else if (len == c) { ++full_pairs; full_prod += len; }
+                else {
+                    ++part_pairs; part_prod += len;
+                    if (iL[ke - 1] - iL[kb] == len - 1) run_prod += len;      // contiguous rows
+                }
+            }
+        }
+        std::fprintf(stderr, "vbk symbolic stats: tasks %zu, (task, contributor) pairs: full %lld, partial %lld, empty %lld; products: full %lld, partial %lld (of which contiguous runs %lld)\n",
+                     task_col.size(), full_pairs, part_pairs, empty_pairs, full_prod, part_prod, run_prod);
     }
 
     // Trailing window treated densely by fast mode.  rho = 1 gives the reference's dense window
