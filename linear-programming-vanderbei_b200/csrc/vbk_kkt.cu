@@ -136,7 +136,8 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
     rk_sig_.upload(sym_.rk_sig, stream_); rj_sig_.upload(sym_.rj_sig, stream_);
     rk_asc_.upload(sym_.rk_asc, stream_); rj_asc_.upload(sym_.rj_asc, stream_);
 
-    L_.alloc(lnz); diag_.alloc(N); mark_.alloc(N); pend_.alloc(N);
+    L_.alloc((size_t)lnz + 2);          // + 2: the strict factor's bulk copies start and end at even entries
+    diag_.alloc(N); mark_.alloc(N); pend_.alloc(N);
     counters_.alloc(C_COUNT); scal_.alloc(S_COUNT); bits_.alloc(S_COUNT);
     z_.alloc(N); xk_.alloc(n); yk_.alloc(m); r_.alloc(m); s_.alloc(n);
     h_dn_.alloc(n); h_dm_.alloc(m); h_c_.alloc(n); h_b_.alloc(m);

@@ -113,48 +113,95 @@ static __global__ void k_pipe_reset(int N, int* __restrict__ col_pub, int* __res
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[C_NEXT] = 0; counters[C_NDEP] = 0; }
 }
 
-// Products of one ring stage.  Written without data-dependent branches: inactive lanes skip their loads by
-// predication, so the loads of a whole batch of contributors are in flight together; the slot of an entry comes from
-// the block's row -> slot map (BLK) or from a branch-free binary search over the task's sorted rows (whole columns).
+// Products of one ring stage, kept lean: a producer warp is bound by its own instruction stream (one warp issues an
+// instruction every few cycles at best), so what counts is instructions per row.
+//  * "full" rows -- the contributor holds every row of the task, the rule in the dense tail -- need neither row indices
+//    nor a zero fill: slot = position.  Eight rows per batch: eight loads in flight, then eight products.
+//  * the other rows are zero-filled (+0.0 where a contributor has no entry) and scattered through the block's row -> slot
+//    map (BLK) or a branch-free binary search over the task's sorted rows (whole columns), eight rows per batch; all
+//    look-ups of a batch come before its first store (a store would fence off the shared-memory loads behind it).
+// fullm / partm / zerom: one bit per contributor of the stage (warp-uniform).
 template <int NCH, bool BLK>
 __device__ __forceinline__ void pipe_products(const PipeArgs& a, const PipeMeta* __restrict__ mp, double* __restrict__ tp,
+                                              unsigned fullm, unsigned partm, unsigned zerom,
                                               const int* __restrict__ blockmap, const int* __restrict__ rows,
                                               int cnt, int bs, int lane)
 {
     constexpr int cap = 32 * NCH;
-    constexpr int QB = 16 / NCH;                                   // contributors whose loads are in flight together
     constexpr int kSteps = (NCH == 1) ? 5 : (NCH == 2 ? 6 : 7);    // log2(cap)
-    for (int q0 = 0; q0 < kPipeQ; q0 += QB) {
-        int ri[QB][NCH];
-        double val[QB][NCH];
+    const double* Lp = a.L + lane;
+    double* tpl = tp + lane;
+    if (fullm) {
+        constexpr int FB = 8 / (NCH > 2 ? 2 : 1);
+#pragma unroll 1
+        for (int q0 = 0; q0 < kPipeQ; q0 += FB) {
+            double wv[FB], val[FB][NCH];
+#pragma unroll
+            for (int u = 0; u < FB; ++u) {
+                if ((fullm >> (q0 + u)) & 1u) {
+                    const PipeMeta m = mp[q0 + u];
+                    wv[u] = m.w;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) val[u][c] = (lane + 32 * c < cnt) ? __ldcg(Lp + m.kb + 32 * c) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FB; ++u) {
+                if ((fullm >> (q0 + u)) & 1u) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+                        if (lane + 32 * c < cnt) tpl[(q0 + u) * cap + 32 * c] = wv[u] * val[u][c];     // lij_dj*AAt[kk], ldlt.c:583
+                }
+            }
+        }
+    }
+    if (zerom) {
+#pragma unroll
+        for (int q = 0; q < kPipeQ; ++q) {
+            if ((zerom >> q) & 1u) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tpl[q * cap + 32 * c] = 0.0;
+            }
+        }
+        __syncwarp();
+    }
+    constexpr int QB = (NCH == 1) ? 4 : (NCH == 2 ? 2 : 1);
+    while (partm) {
+        int qs[QB], lens[QB], ri[QB][NCH], slot[QB][NCH];
+        double wv[QB], val[QB][NCH];
 #pragma unroll
         for (int u = 0; u < QB; ++u) {
-            const PipeMeta m = mp[q0 + u];
+            qs[u] = partm ? __ffs(partm) - 1 : -1;
+            partm &= partm - 1;
+            const PipeMeta m = mp[qs[u] < 0 ? 0 : qs[u]];
+            lens[u] = qs[u] < 0 ? 0 : m.len;
+            wv[u] = m.w;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int e = lane + 32 * c;
                 val[u][c] = 0.0;
                 ri[u][c] = bs;
-                if (e < m.len) { val[u][c] = __ldcg(&a.L[m.kb + e]); ri[u][c] = a.iL[m.kb + e]; }
-                if (m.len != cnt) tp[(q0 + u) * cap + e] = 0.0;    // +0.0 where the contributor has no entry
+                if (e < lens[u]) { val[u][c] = __ldcg(Lp + m.kb + 32 * c); ri[u][c] = a.iL[m.kb + e]; }
             }
         }
-        __syncwarp();
 #pragma unroll
         for (int u = 0; u < QB; ++u) {
-            const PipeMeta m = mp[q0 + u];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const int e = lane + 32 * c;
-                int slot;
-                if (BLK) slot = blockmap[ri[u][c] - bs];
+                if (BLK) slot[u][c] = blockmap[ri[u][c] - bs];
                 else {
-                    slot = 0;                // rows[] is sorted and holds the row: largest s with rows[s] <= row
+                    int sl = 0;              // rows[] is sorted and holds the row: largest s with rows[s] <= row
 #pragma unroll
-                    for (int b2 = kSteps - 1; b2 >= 0; --b2) slot += (rows[slot + (1 << b2)] <= ri[u][c]) ? (1 << b2) : 0;
+                    for (int b2 = kSteps - 1; b2 >= 0; --b2) sl += (rows[sl + (1 << b2)] <= ri[u][c]) ? (1 << b2) : 0;
+                    slot[u][c] = sl;
                 }
-                if (e < m.len) tp[(q0 + u) * cap + slot] = m.w * val[u][c];                // lij_dj*AAt[kk], ldlt.c:583
             }
+        }
+#pragma unroll
+        for (int u = 0; u < QB; ++u) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                if (lane + 32 * c < lens[u]) tp[qs[u] * cap + slot[u][c]] = wv[u] * val[u][c];        // lij_dj*AAt[kk], ldlt.c:583
         }
     }
 }
@@ -181,12 +228,12 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
 
     const double thresh = a.epsnum * bits_to_double(a.scal_bits[S_MAXDIAG]);     // ldlt.c:600
     const int wstride = a.nblk + 1;
-    long long pacc[PROF ? 16 : 1];
+    unsigned pacc[PROF ? 16 : 1];           // 32-bit per lane: enough for one factorisation, half the registers
 #pragma unroll
     for (int u = 0; u < (PROF ? 16 : 1); ++u) pacc[u] = 0;
     long long tlast = PROF ? vbk_clock() : 0;
     const bool profiling = PROF && a.prof != nullptr && lane == 0;
-#define VBK_PTICK(slot) do { if (PROF && profiling) { const long long now_ = vbk_clock(); pacc[PROF ? slot : 0] += now_ - tlast; tlast = now_; } } while (0)
+#define VBK_PTICK(slot) do { if (PROF && profiling) { const long long now_ = vbk_clock(); pacc[PROF ? slot : 0] += (unsigned)(now_ - tlast); tlast = now_; } } while (0)
 
     for (;;) {
         __syncthreads();
@@ -310,7 +357,8 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                 VBK_PTICK(2);
                 // (3) the contributor's column must be final (acquire: the loads below see its final values)
                 if (valid && !flag) {
-                    while (vbk_ld_acquire(&a.col_done[j]) == 0) { __nanosleep(20); vbk_pause(); }
+                    while (vbk_ld_volatile(&a.col_done[j]) == 0) { __nanosleep(20); vbk_pause(); }
+                    (void)vbk_ld_acquire(&a.col_done[j]);
                     lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]);
                 }
                 VBK_PTICK(4);
@@ -330,8 +378,13 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                 __syncwarp();
                 VBK_PTICK(5);
                 // (5) products
-                if (blk >= 0) pipe_products<NCH, true>(a, s_meta + st * kPipeQ, tp, blockmap, rows, cnt, bs, lane);
-                else          pipe_products<NCH, false>(a, s_meta + st * kPipeQ, tp, blockmap, rows, cnt, bs, lane);
+                {
+                    const bool isfull = valid && cnt > 0 && len == cnt;
+                    const unsigned fullm = __ballot_sync(0xffffffffu, isfull);
+                    const unsigned partm = __ballot_sync(0xffffffffu, valid && len > 0 && !isfull);
+                    if (blk >= 0) pipe_products<NCH, true>(a, s_meta + st * kPipeQ, tp, fullm, partm, ~fullm, blockmap, rows, cnt, bs, lane);
+                    else          pipe_products<NCH, false>(a, s_meta + st * kPipeQ, tp, fullm, partm, ~fullm, blockmap, rows, cnt, bs, lane);
+                }
                 VBK_PTICK(6);
                 // (6) next group: entry range, readiness, lij and dj if the column is final already
                 int nkb = nk + 1, nlen = 0, nflag = 1;

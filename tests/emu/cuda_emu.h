@@ -127,6 +127,12 @@ inline int __any_sync(unsigned, int pred) {
     for (int m = 16; m > 0; m >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
     return v;
 }
+inline unsigned __ballot_sync(unsigned, int pred) {
+    unsigned v = pred ? (1u << (threadIdx.x % 32)) : 0u;
+    for (int m = 16; m > 0; m >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
