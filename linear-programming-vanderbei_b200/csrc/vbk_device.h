@@ -71,3 +71,33 @@ __device__ __forceinline__ void vbk_fence_release() {
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
 }
+
+__device__ __forceinline__ void vbk_pause() {      // spin-loop body: yields the OS thread in the host emulation
+#ifdef VBK_EMU
+    sched_yield();
+#endif
+}
+__device__ __forceinline__ void vbk_st_volatile(int* p, int v) {
+#ifdef VBK_EMU
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+    *reinterpret_cast<volatile int*>(p) = v;
+#endif
+}
+// CTA-scope acquire / release on a shared-memory flag (no separate MEMBAR on the waiting side)
+__device__ __forceinline__ int vbk_lds_acquire(const int* p) {
+#ifdef VBK_EMU
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void vbk_sts_release(int* p, int v) {
+#ifdef VBK_EMU
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#endif
+}

@@ -3,6 +3,7 @@
 #include "vbk_kernels.cuh"
 #include "vbk_factor_tiled.cuh"
 #include "vbk_strict_factor.cuh"
+#include "vbk_strict_solve.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -446,7 +447,18 @@ void Kkt::rawsolve_dev()
         VBK_LAUNCH(k_fwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
         VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
         VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
-        VBK_LAUNCH(k_bwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
+        const bool bwd_flags = std::getenv("VBK_BWD") && std::strcmp(std::getenv("VBK_BWD"), "flags") == 0;
+        if (bwd_flags) VBK_LAUNCH(k_bwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
+        else {
+            BwdPipeArgs ba;
+            ba.N = N; ba.nclaim = N; ba.kL = kL_.p; ba.iL = iL_.p; ba.L = L_.p; ba.mark = mark_.p; ba.z = z_.p;
+            ba.done = done_.p; ba.counters = counters_.p; ba.scal_bits = bits_.p; ba.epssol = 1.0e-6;
+            int g = (int)std::max<long long>(1, std::min<long long>((long long)num_sms_ * 6, N));
+#ifdef VBK_EMU
+            g = std::min(g, 3);
+#endif
+            VBK_LAUNCH(k_bwd_pipe, g, kBwdWarps * 32, bwd_pipe_smem_bytes(), stream_, ba);
+        }
         VBK_CHECK_LAUNCH();
         stats.kernel_launches += 7;
         return;

@@ -94,19 +94,6 @@ __device__ __forceinline__ long long vbk_globaltimer() {
     return t;
 #endif
 }
-__device__ __forceinline__ void vbk_pause() {
-#ifdef VBK_EMU
-    sched_yield();
-#endif
-}
-__device__ __forceinline__ void vbk_st_volatile(int* p, int v) {
-#ifdef VBK_EMU
-    __atomic_store_n(p, v, __ATOMIC_RELEASE);
-#else
-    *reinterpret_cast<volatile int*>(p) = v;
-#endif
-}
-
 static __global__ void k_pipe_reset(int N, int* __restrict__ col_pub, int* __restrict__ col_done, int* __restrict__ counters)
 {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) { col_pub[t] = 0; col_done[t] = 0; }
