@@ -36,8 +36,10 @@ def shard(nlp: int, rank: int, world: int):
     return list(range(rank, nlp, world))
 
 
-def solve_local(lib, lps, method="hsd", device=0, mode=1, nstreams=4):
-    """Solve ``lps`` (objects with m, n, nz, kA, iA, A, b, c, f) on one GPU.  Returns a list of dicts
+def solve_local(lib, lps, method="hsd", device=0, mode=0, nstreams=4):
+    """Solve ``lps`` (objects with m, n, nz, kA, iA, A, b, c, f) on one GPU.  ``mode`` 0 = strict (the reference's
+    arithmetic, bit for bit -- the mode that carries the parity claim, and the default), 1 = fast (opt in: dense-window
+    factorisation, tolerance parity only).  Returns a list of dicts
     (status, iterations, primal_obj, dual_obj, seconds, x, y) in input order."""
     declare(lib)
     keep, descs = [], (LpDesc * max(len(lps), 1))()
@@ -58,7 +60,7 @@ def solve_local(lib, lps, method="hsd", device=0, mode=1, nstreams=4):
             for d, a in zip(descs, keep)]
 
 
-def solve_batch(lib, make_lp, nlp, method="hsd", device=0, mode=1, nstreams=4, group=None, result_device="cpu"):
+def solve_batch(lib, make_lp, nlp, method="hsd", device=0, mode=0, nstreams=4, group=None, result_device="cpu"):
     """Distributed batch solve.  ``make_lp(i)`` builds LP ``i`` (only called for the LPs this rank owns,
     so generators run sharded too).  Returns (summary[nlp, 5] = status, iterations, primal_obj, dual_obj,
     seconds for every LP of the batch, local_results)."""

@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 SOURCES = ["vbk_symbolic.cpp", "vbk_kkt.cu", "vbk_kkt_fast.cu", "vbk_linalg.cu", "vbk_solver.cu", "vbk_batch.cu", "vbk_rowblock.cu", "vbk_capi.cu"]
-HEADERS = ["vbk_symbolic.h", "vbk_strict_factor.cuh", "vbk_strict_solve.cuh", "vbk_kkt.h", "vbk_linalg.h", "vbk_solver.h", "vbk_kernels.cuh", "vbk_factor_tiled.cuh", "vbk_fast.cuh", "vbk_fast2.cuh", "vbk_fast3.cuh", "vbk_fast4.cuh", "vbk_fast5.cuh", "vbk_fast6.cuh", "vbk_device.h"]
+HEADERS = sorted(p.name for p in CSRC.glob("*.h")) + sorted(p.name for p in CSRC.glob("*.cuh"))
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",                       # strict mode: no FMA contraction on the device

@@ -1,10 +1,8 @@
-// vbk_fast3.cuh -- third-generation dense-window factorisation (fast mode): 128-column panels.
+// vbk_dense_panel.cuh -- dense-window factorisation (fast mode): 128-column panels.
 //
-// Measured on B200 with the kernels of vbk_fast2.cuh (dfl001, padded window W=4277): 13.5 of the 16.9 ms
-// of a factorisation are the 134 x (k_dense_diag_w, k_dense_trsm_u, strip update) launches of the
-// 32-column panels -- a chain of ~400 small dependent kernels, ~100 us per panel, while the rank-128
-// trailing updates that hold nearly all the flops take ~1.5 ms.  Here a panel is 128 columns and costs
-// three launches in all:
+// A panel is 128 columns and costs three launches in all (the 32-column panels of the first generations were a chain
+// of ~400 small dependent kernels, ~100 us per panel on dfl001, while the rank-128 updates that hold nearly all the
+// flops took ~1.5 ms):
 //   k_panel_diag  ONE CTA factorises the 128 x 128 diagonal block in shared memory: four 32-column
 //                 sub-blocks, each = warp-level LDL^T in registers (warp 0), row-parallel substitution for
 //                 the block rows below it, rank-32 update of the rest of the block (all warps);
@@ -13,13 +11,13 @@
 //                 memory as ONE bulk asynchronous copy (cp.async.bulk + mbarrier) of the packed panel buffer
 //                 the diagonal kernel leaves behind; per sub-block a rank-(32b) update from the row's own
 //                 earlier results, then four 8-column substitution stages chained by quad shuffles;
-//   k_dense_update_k  (vbk_fast2.cuh) the rank-128 update of the trailing matrix.
+//   k_dense_update_m  (vbk_dense_update.cuh) the rank-128 update of the trailing matrix on the FP64 tensor path.
 // The dependent-pivot rule (reference ldlt.c:600-614) keeps its meaning: when a pivot is "zero" the
 // maximum of the updated column below it decides between dropping the row and substituting the pivot;
 // rows whose panel columns have not been touched yet get them applied on the fly by the whole CTA
 // (rare path, O(rows * c^2)).
 #pragma once
-#include "vbk_fast2.cuh"
+#include "vbk_dense_common.cuh"
 
 namespace vbk {
 
@@ -235,20 +233,18 @@ __device__ __forceinline__ void panel_inverse32(const DenseArgs& a, const double
 }
 #endif
 
-// Ordering point between a lane's store into the column ring and the other lanes' loads.  In the optimistic pass the
-// warp runs straight-line code (selects, no branches) from one __syncwarp at entry, so its lanes execute every
-// instruction together and the in-order shared-memory pipe orders the store before the loads; a compiler-level fence
-// is all that is needed.  A real __syncwarp() here costs ~200 cycles per column: the compiler cannot prove convergence,
-// emits a divergence check and re-derives the shared-memory window base (S2UR SR_CgaCtaId) after every one of them,
-// right on the dependent chain (cuobjdump: 33 BRA.DIV + 57 S2UR in the kernel, none in scratch/ubench2.cu, which runs the
-// same loop at 127 cycles per column).  The pass with the rare path (branches, a call) keeps the real barrier.
+// Ordering point between a lane's store into the column ring and the other lanes' loads: a real warp barrier
+// (bar.warp.sync orders the participating lanes' shared-memory accesses; lockstep execution of straight-line code is
+// not something CUDA guarantees under independent thread scheduling).  The optimistic pass issues the barrier as inline
+// PTX: __syncwarp() there made the compiler emit a divergence check and re-derive the shared-memory window base
+// (S2UR SR_CgaCtaId) after every one of them, right on the dependent chain.
 template <bool kRare> __device__ __forceinline__ void ldl_fence()
 {
 #ifdef VBK_EMU
     __syncwarp();
 #else
     if (kRare) __syncwarp();
-    else asm volatile("" ::: "memory");
+    else asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
 #endif
 }
 

@@ -21,12 +21,10 @@ namespace vbk {
 
 #ifdef VBK_EMU
 // the host emulation spawns one OS thread per CUDA thread: keep CTAs small there
-constexpr int kFactorThreads = 32;
 constexpr int kSolveThreads = 32;
 constexpr int kVecThreads = 32;
 constexpr int kScanThreads = 32;
 #else
-constexpr int kFactorThreads = 256;   // CTA size of the strict factor kernel
 constexpr int kSolveThreads = 128;    // 4 warps per CTA in the dataflow solve kernels
 constexpr int kVecThreads = 256;
 constexpr int kScanThreads = 1024;
@@ -103,137 +101,6 @@ static __global__ void k_scatter(int nz, const int* __restrict__ map, const doub
     }
 }
 
-// resets the per-launch dataflow state: pend[] <- init (etree child counts, or all ones)
-// flags: bit0 clears the dependent-pivot count, bit1 sets rawsolve's consistency flag to TRUE
-static __global__ void k_reset_pend(int N, const int* __restrict__ init, int fill, int* __restrict__ pend,
-                             int* __restrict__ counters, int flags)
-{
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x)
-        pend[t] = init ? init[t] : fill;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        counters[C_NEXT] = 0;
-        if (flags & 1) counters[C_NDEP] = 0;
-        if (flags & 2) counters[C_CONSISTENT] = 1;
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// K2/K4  numeric LDL^T, strict: left-looking by column in the reference's accumulation order
-// (lltnum, ldlt.c:565-631).  One CTA per column; the list (rk,rj) of row i, in the order lltnum's
-// link lists visit it, gives for each contributing column j the position k of L[i,j]; the rows
-// of column j below i follow at k+1...  Threads split those rows; contributors are applied one
-// after the other so every temp[] entry sees the reference's sequence of rounded adds.
-// --------------------------------------------------------------------------------------------
-struct FactorArgs {
-    int N, n_ld, maxcol, smem_slots;
-    const int* kL; const int* iL; double* L; double* diag; int* mark;
-    const int* rowptr; const int* rk; const int* rj;
-    const int* parent; const int* perm;
-    int* pend; int* counters;
-    const unsigned long long* scal_bits;
-    double epsnum;
-    int* slotmap;      // [gridDim.x][N]   row -> slot in the current column
-    double* gtemp;     // [gridDim.x][maxcol] accumulator for columns longer than smem_slots
-};
-
-static __global__ void __launch_bounds__(kFactorThreads) k_factor_strict(FactorArgs a)
-{
-    VBK_DYN_SMEM(raw);
-    double* s_temp = reinterpret_cast<double*>(raw);
-    double* s_w = s_temp + a.smem_slots;          // lij*dj of the staged contributors
-    double* s_l = s_w + kFactorThreads;           // lij
-    double* s_red = s_l + kFactorThreads;         // reduction scratch
-    double* s_dbl = s_red + kFactorThreads;       // [0] pivot
-    int* s_kb = reinterpret_cast<int*>(s_dbl + 2);
-    int* s_ke = s_kb + kFactorThreads;
-    int* s_ctl = s_ke + kFactorThreads;           // [0] column, [1] dependent flag, [2] mark
-
-    const int tid = threadIdx.x, nt = blockDim.x;
-    int* myslot = a.slotmap + (size_t)blockIdx.x * a.N;
-    double* mytemp = a.gtemp + (size_t)blockIdx.x * a.maxcol;
-    const double thresh = a.epsnum * bits_to_double(a.scal_bits[S_MAXDIAG]);   // ldlt.c:600
-
-    for (;;) {
-        if (tid == 0) s_ctl[0] = atomicAdd(&a.counters[C_NEXT], 1);
-        __syncthreads();
-        const int i = s_ctl[0];
-        if (i >= a.N) break;
-        const int cb = a.kL[i], ci = a.kL[i + 1] - cb;
-        double* temp = (ci <= a.smem_slots) ? s_temp : mytemp;
-        for (int q = tid; q < ci; q += nt) { temp[q] = 0.0; myslot[a.iL[cb + q]] = q; }
-
-        // wait until every elimination-tree child (hence every contributing column) is final
-        if (tid == 0) {
-            while (vbk_ld_volatile(&a.pend[i]) != 0) __nanosleep(64);
-            __threadfence();
-        }
-        __syncthreads();
-
-        double diagi = 0.0;
-        if (tid == 0) diagi = __ldcg(&a.diag[i]);
-        const int rb = a.rowptr[i], re = a.rowptr[i + 1];
-        for (int t0 = rb; t0 < re; t0 += nt) {
-            const int cnt = (re - t0 < nt) ? (re - t0) : nt;
-            if (tid < cnt) {                       // stage up to nt contributors at once
-                int k = a.rk[t0 + tid], j = a.rj[t0 + tid];
-                double lij = __ldcg(&a.L[k]);
-                double dj = __ldcg(&a.diag[j]);
-                s_l[tid] = lij;
-                s_w[tid] = lij * dj;               // lij_dj, ldlt.c:572
-                s_kb[tid] = k + 1;
-                s_ke[tid] = a.kL[j + 1];
-            }
-            __syncthreads();
-            for (int q = 0; q < cnt; ++q) {
-                const double w = s_w[q];
-                const int kb = s_kb[q], ke = s_ke[q];
-                if (tid == 0) diagi -= s_l[q] * w;                       // ldlt.c:573
-                for (int kk = kb + tid; kk < ke; kk += nt) {
-                    int sl = myslot[a.iL[kk]];
-                    temp[sl] += w * __ldcg(&a.L[kk]);                     // ldlt.c:583/588
-                }
-                __syncthreads();   // next contributor may touch the same slots from other threads
-            }
-        }
-
-        // L[:,i] -= temp (ldlt.c:596-599); keep the updated column in temp for the pivot rule
-        double mymax = 0.0;
-        for (int q = tid; q < ci; q += nt) {
-            double v = __ldcg(&a.L[cb + q]) - temp[q];
-            temp[q] = v;
-            double av = vbk_abs(v);
-            if (av > mymax) mymax = av;
-        }
-        if (tid == 0) {
-            s_ctl[1] = (fabs(diagi) <= thresh) ? 1 : 0;   // mark[i] is TRUE here (ldlt.c:280)
-            s_ctl[2] = 1;
-            s_dbl[0] = diagi;
-        }
-        s_red[tid] = mymax;
-        __syncthreads();
-        if (s_ctl[1]) {                                   // dependent pivot, ldlt.c:600-614
-            for (int s = nt / 2; s > 0; s >>= 1) {
-                if (tid < s && s_red[tid + s] > s_red[tid]) s_red[tid] = s_red[tid + s];
-                __syncthreads();
-            }
-            if (tid == 0) {
-                atomicAdd(&a.counters[C_NDEP], 1);
-                if (s_red[0] < 1.0e+6 * 1.0e-8) s_ctl[2] = 0;
-                else s_dbl[0] = (a.perm[i] < a.n_ld ? -1 : 1) * 1.0e-8;
-            }
-            __syncthreads();
-        }
-        const double piv = s_dbl[0];
-        const int keep = s_ctl[2];
-        if (tid == 0) { a.diag[i] = piv; if (!keep) a.mark[i] = 0; }
-        for (int q = tid; q < ci; q += nt) a.L[cb + q] = keep ? temp[q] / piv : 0.0;   // ldlt.c:621-627
-
-        __threadfence();          // publish column i before releasing the parent
-        __syncthreads();
-        if (tid == 0) { int p = a.parent[i]; if (p >= 0) atomicSub(&a.pend[p], 1); }
-    }
-}
-
 // mindiag < 1e-14  =>  epsdiag *= 10 (ldlt.c:293-306).  Two tiny kernels: reduction, then update.
 static __global__ void k_min_absdiag(int N, const double* __restrict__ diag, unsigned long long* __restrict__ scal_bits)
 {
@@ -271,7 +138,7 @@ struct SolveArgs {
     const int* rowptr; const int* rk; const int* rj;   // ascending lists
     const int* parent;
     double* z;
-    int* pend; int* counters;
+    int* counters;
     const unsigned long long* scal_bits;
     double epssol;
 };
@@ -279,49 +146,6 @@ struct SolveArgs {
 __device__ __forceinline__ double solve_eps(const SolveArgs& a) {
     // ldlt.c:446: if (ndep) eps = epssol * maxv(z,m)
     return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;
-}
-
-static __global__ void __launch_bounds__(kSolveThreads) k_fwd_strict(SolveArgs a)
-{
-    const int lane = threadIdx.x & 31;
-    const double eps = solve_eps(a);
-    for (;;) {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(&a.counters[C_NEXT], 1);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= a.N) break;
-        if (lane == 0) {
-            while (vbk_ld_volatile(&a.pend[r]) != 0) __nanosleep(32);
-            __threadfence();
-        }
-        __syncwarp();
-        double acc = __ldcg(&a.z[r]);
-        const int rb = a.rowptr[r], re = a.rowptr[r + 1];
-        for (int t0 = rb; t0 < re; t0 += 32) {
-            int t = t0 + lane;
-            double p = 0.0;
-            int ok = 0;
-            if (t < re) {
-                int j = a.rj[t];
-                if (a.mark[j]) { p = __ldcg(&a.L[a.rk[t]]) * __ldcg(&a.z[j]); ok = 1; }
-            }
-            const int cnt = (re - t0 < 32) ? (re - t0) : 32;
-            for (int q = 0; q < cnt; ++q) {
-                double pq = __shfl_sync(0xffffffffu, p, q);
-                int okq = __shfl_sync(0xffffffffu, ok, q);
-                if (okq) acc = acc - pq;                        // z[row] -= AAt[k]*beta, ldlt.c:459
-            }
-        }
-        if (lane == 0) {
-            if (a.mark[r]) a.z[r] = acc;
-            else if (fabs(acc) > eps) { a.z[r] = acc; a.counters[C_CONSISTENT] = 0; }
-            else a.z[r] = 0.0;
-            __threadfence();
-            int p = a.parent[r];
-            if (p >= 0) atomicSub(&a.pend[p], 1);
-        }
-        __syncwarp();
-    }
 }
 
 static __global__ void k_diag_strict(SolveArgs a)
@@ -332,48 +156,6 @@ static __global__ void k_diag_strict(SolveArgs a)
         if (a.mark[i]) a.z[i] = v / a.diag[i];                  // ldlt.c:476
         else if (fabs(v) > eps) a.counters[C_CONSISTENT] = 0;
         else a.z[i] = 0.0;
-    }
-}
-
-// Backward: z[i] = z[i] - sum_k L[k]*z[row_k] in ascending k (ldlt.c:490-496); column i needs
-// every ancestor final, which the parent's completion implies.  Columns are claimed in
-// DESCENDING order; pend[i]==0 means "column i done" here.
-static __global__ void __launch_bounds__(kSolveThreads) k_bwd_strict(SolveArgs a)
-{
-    const int lane = threadIdx.x & 31;
-    const double eps = solve_eps(a);
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&a.counters[C_NEXT], 1);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= a.N) break;
-        const int i = a.N - 1 - c;
-        const int par = a.parent[i];
-        if (lane == 0 && par >= 0) {
-            while (vbk_ld_volatile(&a.pend[par]) != 0) __nanosleep(32);
-            __threadfence();
-        }
-        __syncwarp();
-        double beta = __ldcg(&a.z[i]);
-        if (a.mark[i]) {
-            const int kb = a.kL[i], ke = a.kL[i + 1];
-            for (int k0 = kb; k0 < ke; k0 += 32) {
-                int k = k0 + lane;
-                double p = 0.0;
-                if (k < ke) p = a.L[k] * __ldcg(&a.z[a.iL[k]]);
-                const int cnt = (ke - k0 < 32) ? (ke - k0) : 32;
-                for (int q = 0; q < cnt; ++q) beta = beta - __shfl_sync(0xffffffffu, p, q);
-            }
-            if (lane == 0) a.z[i] = beta;
-        } else if (lane == 0) {
-            if (fabs(beta) > eps) a.counters[C_CONSISTENT] = 0;
-            else a.z[i] = 0.0;
-        }
-        if (lane == 0) {
-            __threadfence();
-            atomicExch(&a.pend[i], 0);
-        }
-        __syncwarp();
     }
 }
 

@@ -1,7 +1,6 @@
 // vbk_kkt.cu -- host orchestration of the device-resident factor object (see vbk_kkt.h).
 #include "vbk_kkt.h"
 #include "vbk_kernels.cuh"
-#include "vbk_factor_tiled.cuh"
 #include "vbk_strict_factor.cuh"
 #include "vbk_strict_solve.cuh"
 
@@ -76,14 +75,9 @@ Kkt::~Kkt()
     for (int u = 0; u < 2; ++u) {
         if (ev_rows_[u]) cudaEventDestroy(ev_rows_[u]);
         if (ev_updb_[u]) cudaEventDestroy(ev_updb_[u]);
-        if (ev_diag_[u]) cudaEventDestroy(ev_diag_[u]);
-        if (ev_rowsa_[u]) cudaEventDestroy(ev_rowsa_[u]);
-        if (ev_rowsb_[u]) cudaEventDestroy(ev_rowsb_[u]);
-        if (ev_stripb_[u]) cudaEventDestroy(ev_stripb_[u]);
     }
 #ifndef VBK_EMU
     if (stream2_) cudaStreamDestroy(stream2_);
-    if (stream3_) cudaStreamDestroy(stream3_);
     if (stream_) cudaStreamDestroy(stream_);
 #endif
 }
@@ -138,7 +132,7 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
     rk_asc_.upload(sym_.rk_asc, stream_); rj_asc_.upload(sym_.rj_asc, stream_);
 
     L_.alloc((size_t)lnz + 2);          // + 2: the strict factor's bulk copies start and end at even entries
-    diag_.alloc(N); mark_.alloc(N); pend_.alloc(N);
+    diag_.alloc(N); mark_.alloc(N);
     counters_.alloc(C_COUNT); scal_.alloc(S_COUNT); bits_.alloc(S_COUNT);
     z_.alloc(N); xk_.alloc(n); yk_.alloc(m); r_.alloc(m); s_.alloc(n);
     h_dn_.alloc(n); h_dm_.alloc(m); h_c_.alloc(n); h_b_.alloc(m);
@@ -149,78 +143,31 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
     VBK_CUDA(cudaMemsetAsync(bits_.p, 0, sizeof(unsigned long long) * S_COUNT, stream_));
     VBK_CUDA(cudaMemsetAsync(counters_.p, 0, sizeof(int) * C_COUNT, stream_));
 
-    // launch geometry of the persistent dataflow kernels
-    smem_slots_ = 4096;
-    factor_smem_ = sizeof(double) * ((size_t)smem_slots_ + 3 * kFactorThreads + 2) +
-                   sizeof(int) * (2 * kFactorThreads + 4);
-    int occ = 1;
-    VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_strict, kFactorThreads, factor_smem_));
-    occ = std::max(1, std::min(occ, 4));
-    long long grid = (long long)num_sms_ * occ;
-    const long long budget = (long long)6 << 30;         // bytes of per-CTA scratch we allow
-    long long per_cta = (long long)N * 4 + (long long)sym_.maxcol * 8;
-    if (grid * per_cta > budget) grid = std::max<long long>(num_sms_ / 2, budget / per_cta);
-    grid = std::max<long long>(1, std::min<long long>(grid, N));
-    factor_grid_ = (int)grid;
-#ifdef VBK_EMU
-    factor_grid_ = std::max(1, std::min(3, N));   // several CTAs, so the dataflow waits are exercised
-#endif
-    slotmap_.alloc((size_t)factor_grid_ * N);
-    gtemp_.alloc((size_t)factor_grid_ * std::max(sym_.maxcol, 1));
     solve_grid_ = (int)std::max<long long>(1, std::min<long long>((long long)num_sms_ * 8, ((long long)N + 3) / 4));
 #ifdef VBK_EMU
     solve_grid_ = std::min(solve_grid_, 3);
 #endif
 
-    // second-generation strict kernels: task tables, pivot hand-off arrays, launch geometry
+    // slice tasks of the numeric factorisation (vbk_symbolic.h)
     {
-        const char* ef = std::getenv("VBK_FACTOR");
-        const char* es = std::getenv("VBK_SOLVE");
-        use_tiled_ = !(ef && std::strcmp(ef, "simple") == 0);
-        use_flags_ = !(es && std::strcmp(es, "simple") == 0);
         const int ntasks = sym_.ntasks();
-        int max_slices = 1, max_cnt = 1;
-        for (int j = 0; j < N; ++j) max_slices = std::max(max_slices, sym_.col_ntask[j]);
-        for (int t = 0; t < ntasks; ++t) max_cnt = std::max(max_cnt, sym_.task_cnt[t]);
         task_col_.upload(sym_.task_col, stream_); task_blk_.upload(sym_.task_blk, stream_);
         task_pos0_.upload(sym_.task_pos0, stream_); task_cnt_.upload(sym_.task_cnt, stream_);
         col_task0_.upload(sym_.col_task0, stream_); col_ntask_.upload(sym_.col_ntask, stream_);
         if (!sym_.winptr.empty()) winptr_.upload(sym_.winptr, stream_); else winptr_.alloc(1);
-        col_left_.alloc(N); col_ready_.alloc(N); piv_flag_.alloc(N); piv_keep_.alloc(N); done_.alloc(N);
-        piv_val_.alloc(N); task_max_.alloc(std::max(ntasks, 1));
-        if (std::getenv("VBK_PROF")) { prof_.alloc(16); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 128, stream_)); }
-        temp_cap_ = std::max(max_cnt, 32);
-        tile_doubles_ = std::max(8192, temp_cap_);
-        tiled_smem_ = sizeof(double) * ((size_t)tile_doubles_ + temp_cap_ + 2 * kTileMaxBatch + kTiledThreads + 2) +
-                      sizeof(int) * ((size_t)2 * kTileMaxBatch + 1 + sym_.rowblk + 8);
-#ifndef VBK_EMU
-        // the cap is per FUNCTION, not per handle: concurrent handles (batch driver) need different sizes, so the
-        // cap is always raised to the device maximum and never lowered
-        VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
-#endif
-        int occ2 = 1;
-        VBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_factor_tiled, kTiledThreads, tiled_smem_));
-        occ2 = std::max(1, std::min(occ2, 3));
-        long long g2 = (long long)num_sms_ * occ2;
-        if (g2 * (long long)N * 4 > budget) g2 = std::max<long long>(num_sms_ / 2, budget / ((long long)N * 4));
-        g2 = std::max<long long>(1, std::min<long long>(g2, ntasks));
-#ifdef VBK_EMU
-        g2 = std::max(1, std::min(3, ntasks));
-#endif
-        // a dependent pivot makes the first slice of a column wait for all its sibling slices, so
-        // every slice of one column must be able to be resident at the same time
-        g2 = std::max<long long>(g2, std::min<long long>(ntasks, max_slices + 1));
-        tiled_grid_ = (int)g2;
-        if ((size_t)tiled_grid_ > (size_t)factor_grid_) slotmap_.alloc((size_t)tiled_grid_ * N);
+        done_.alloc(N); task_max_.alloc(std::max(ntasks, 1));
     }
-    // third-generation strict factor kernel: launch geometry
+    // strict factor kernel (vbk_strict_factor.cuh): launch geometry
     {
-        const char* ef = std::getenv("VBK_FACTOR");
         const int ntasks = sym_.ntasks();
         int max_cnt = 1;
         for (int t = 0; t < ntasks; ++t) max_cnt = std::max(max_cnt, sym_.task_cnt[t]);
         pipe_cap_ = max_cnt <= 32 ? 32 : (max_cnt <= 64 ? 64 : 128);
-        use_pipe_ = use_tiled_ && !(ef && std::strcmp(ef, "tiled") == 0) && max_cnt <= 32 * kPipeMaxChains;
+        if (max_cnt > 32 * kPipeMaxChains) {
+            std::fprintf(stderr, "vbkkt: a slice task of %d rows exceeds the factor kernel's %d; raise the row-block limit\n",
+                         max_cnt, 32 * kPipeMaxChains);
+            std::exit(1);
+        }
         pipe_warps_ = kPipeWarpsDefault;
 #ifndef VBK_EMU
         if (const char* e = std::getenv("VBK_PIPE_WARPS")) pipe_warps_ = std::max(3, std::min(kPipeWarpsDefault, std::atoi(e)));
@@ -229,8 +176,11 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
         if (const char* e = std::getenv("VBK_PIPE_STAGES")) pipe_stages_ = std::max(2, std::min(16, std::atoi(e)));
         while (pipe_stages_ > 2 && pipe_smem_bytes(pipe_cap_, pipe_stages_, sym_.rowblk, pipe_warps_) > (size_t)smem_optin_) --pipe_stages_;
         pipe_smem_ = pipe_smem_bytes(pipe_cap_, pipe_stages_, sym_.rowblk, pipe_warps_);
-        if (pipe_smem_ > (size_t)smem_optin_) use_pipe_ = false;
-        if (use_pipe_) {
+        if (pipe_smem_ > (size_t)smem_optin_) {
+            std::fprintf(stderr, "vbkkt: the strict factor kernel needs %zu bytes of shared memory, the device offers %d\n", pipe_smem_, smem_optin_);
+            std::exit(1);
+        }
+        {
             col_pub_.alloc(N); col_done_.alloc(N);
             int occ3 = 1;
 #ifndef VBK_EMU
@@ -256,11 +206,11 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
     VBK_CUDA(cudaStreamSynchronize(stream_));
 }
 
-void Kkt::launch_factor_pipe()
+void Kkt::launch_factor_pipe(int ntasks, bool timed)
 {
     const int N = sym_.N;
     PipeArgs pa;
-    pa.N = N; pa.n_ld = sym_.n; pa.ntasks = sym_.ntasks(); pa.nstages = pipe_stages_;
+    pa.N = N; pa.n_ld = sym_.n; pa.ntasks = ntasks; pa.nstages = pipe_stages_;
     pa.kL = kL_.p; pa.iL = iL_.p; pa.L = L_.p; pa.diag = diag_.p; pa.mark = mark_.p;
     pa.rowptr = rowptr_.p; pa.rk = rk_sig_.p; pa.rj = rj_sig_.p; pa.perm = perm_.p;
     pa.task_col = task_col_.p; pa.task_blk = task_blk_.p; pa.task_pos0 = task_pos0_.p; pa.task_cnt = task_cnt_.p;
@@ -275,17 +225,18 @@ void Kkt::launch_factor_pipe()
     if (debug_) std::fprintf(stderr, "vbk factor: pipe kernel, grid %d, %d warps, %d stages, cap %d, smem %zu, %d tasks\n",
                              pipe_grid_, pipe_warps_, pipe_stages_, pipe_cap_, pipe_smem_, pa.ntasks);
     VBK_LAUNCH(k_pipe_reset, vec_grid(N), kVecThreads, 0, stream_, N, col_pub_.p, col_done_.p, counters_.p);
-    VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
+    const int grid = std::max(1, std::min(pipe_grid_, ntasks));
+    if (timed) VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
     if (pa.prof) {
-        if (pipe_cap_ == 32) VBK_LAUNCH((k_factor_pipe<1, true>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
-        else if (pipe_cap_ == 64) VBK_LAUNCH((k_factor_pipe<2, true>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
-        else VBK_LAUNCH((k_factor_pipe<4, true>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        if (pipe_cap_ == 32) VBK_LAUNCH((k_factor_pipe<1, true>), grid, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else if (pipe_cap_ == 64) VBK_LAUNCH((k_factor_pipe<2, true>), grid, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else VBK_LAUNCH((k_factor_pipe<4, true>), grid, pipe_warps_ * 32, pipe_smem_, stream_, pa);
     } else {
-        if (pipe_cap_ == 32) VBK_LAUNCH((k_factor_pipe<1, false>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
-        else if (pipe_cap_ == 64) VBK_LAUNCH((k_factor_pipe<2, false>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
-        else VBK_LAUNCH((k_factor_pipe<4, false>), pipe_grid_, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        if (pipe_cap_ == 32) VBK_LAUNCH((k_factor_pipe<1, false>), grid, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else if (pipe_cap_ == 64) VBK_LAUNCH((k_factor_pipe<2, false>), grid, pipe_warps_ * 32, pipe_smem_, stream_, pa);
+        else VBK_LAUNCH((k_factor_pipe<4, false>), grid, pipe_warps_ * 32, pipe_smem_, stream_, pa);
     }
-    VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
+    if (timed) VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
 }
 
 void Kkt::read_scalars()
@@ -348,71 +299,20 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
     VBK_CUDA(cudaMemsetAsync(L_.p, 0, sizeof(double) * (size_t)lnz, stream_));
     VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapA_.p, A_val_.p, L_.p);
     VBK_LAUNCH(k_scatter, vec_grid(nz), kVecThreads, 0, stream_, nz, mapAt_.p, At_val_.p, L_.p);
-    if (use_pipe_ && !(mode_ == kFast && sym_.dense_start < N && fast_ready_)) {
-        // K2/K4 numeric LDL^T, pipelined slice tasks (vbk_strict_factor.cuh)
-        launch_factor_pipe();
-        VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);
-        VBK_LAUNCH(k_update_epsdiag, 1, 32, 0, stream_, scal_.p, bits_.p);
-        VBK_CHECK_LAUNCH();
-        stats.kernel_launches += 9;
-        return;
-    }
-    if (use_tiled_) {
-        // K2/K4 numeric LDL^T, batched-tile / sliced-column kernel (vbk_factor_tiled.cuh)
-        VBK_LAUNCH(k_tiled_reset, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, col_ntask_.p, pend_.p,
-                   col_left_.p, col_ready_.p, piv_flag_.p, counters_.p);
-        TiledArgs ta;
-        fill_tiled_args(ta);
+    // K2/K4 numeric LDL^T (lltnum, ldlt.c:565-631): pipelined slice tasks (vbk_strict_factor.cuh); fast mode keeps
+    // them for the sparse columns only and factorises the trailing window densely (vbk_kkt_fast.cu)
+    if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
         VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
-        if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
-            factor_window_fast(ta);               // sparse part + Schur assembly + dense window (vbk_kkt_fast.cu)
-        } else {
-            VBK_LAUNCH(k_factor_tiled, tiled_grid_, kTiledThreads, tiled_smem_, stream_, ta);
-        }
+        factor_window_fast();
         VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
-        VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);
-        VBK_LAUNCH(k_update_epsdiag, 1, 32, 0, stream_, scal_.p, bits_.p);
-        VBK_CHECK_LAUNCH();
-        stats.kernel_launches += 9;
-        return;
+    } else {
+        launch_factor_pipe(sym_.ntasks(), true);
     }
-    VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, 0, pend_.p, counters_.p, 1);
-
-    // K2/K4 numeric LDL^T, first-generation kernel (one barrier per contributor)
-    FactorArgs fa;
-    fa.N = N; fa.n_ld = n; fa.maxcol = std::max(sym_.maxcol, 1); fa.smem_slots = smem_slots_;
-    fa.kL = kL_.p; fa.iL = iL_.p; fa.L = L_.p; fa.diag = diag_.p; fa.mark = mark_.p;
-    fa.rowptr = rowptr_.p; fa.rk = rk_sig_.p; fa.rj = rj_sig_.p;
-    fa.parent = parent_.p; fa.perm = perm_.p;
-    fa.pend = pend_.p; fa.counters = counters_.p; fa.scal_bits = bits_.p;
-    fa.epsnum = 0.0;                                       // _EPSNUM, ldlt.c:29
-    fa.slotmap = slotmap_.p; fa.gtemp = gtemp_.p;
-    VBK_CUDA(cudaEventRecord(ev_f0_, stream_));
-    VBK_LAUNCH(k_factor_strict, factor_grid_, kFactorThreads, factor_smem_, stream_, fa);
-    VBK_CUDA(cudaEventRecord(ev_f1_, stream_));
-
     // epsdiag escalation (ldlt.c:293-306)
     VBK_LAUNCH(k_min_absdiag, vec_grid(N), kVecThreads, 0, stream_, N, diag_.p, bits_.p);
     VBK_LAUNCH(k_update_epsdiag, 1, 32, 0, stream_, scal_.p, bits_.p);
     VBK_CHECK_LAUNCH();
     stats.kernel_launches += 9;
-}
-
-void Kkt::fill_tiled_args(TiledArgs& ta)
-{
-    ta.N = sym_.N; ta.n_ld = sym_.n; ta.ntasks = sym_.ntasks(); ta.tile_doubles = tile_doubles_; ta.temp_cap = temp_cap_;
-    ta.kL = kL_.p; ta.iL = iL_.p; ta.L = L_.p; ta.diag = diag_.p; ta.mark = mark_.p;
-    ta.rowptr = rowptr_.p; ta.rk = rk_sig_.p; ta.rj = rj_sig_.p;
-    ta.parent = parent_.p; ta.perm = perm_.p;
-    ta.task_col = task_col_.p; ta.task_blk = task_blk_.p; ta.task_pos0 = task_pos0_.p; ta.task_cnt = task_cnt_.p;
-    ta.col_task0 = col_task0_.p; ta.col_ntask = col_ntask_.p;
-    ta.winptr = winptr_.p; ta.nblk = sym_.nblk; ta.rowblk = sym_.rowblk; ta.slice_row0 = sym_.slice_row0;
-    ta.pend = pend_.p; ta.col_left = col_left_.p; ta.col_ready = col_ready_.p; ta.piv_flag = piv_flag_.p;
-    ta.piv_val = piv_val_.p; ta.piv_keep = piv_keep_.p; ta.task_max = task_max_.p;
-    ta.counters = counters_.p; ta.scal_bits = bits_.p; ta.epsnum = 0.0;       // _EPSNUM, ldlt.c:29
-    ta.slotmap = slotmap_.p;
-    ta.prof = prof_.p;
-    ta.phase = 0; ta.task_base = 0; ta.T = sym_.N; ta.ldw = 0; ta.Sw = nullptr; ta.wmag = nullptr;
 }
 
 void Kkt::rawsolve_dev()
@@ -424,50 +324,38 @@ void Kkt::rawsolve_dev()
     sa.N = N; sa.m_ld = sym_.m;
     sa.kL = kL_.p; sa.iL = iL_.p; sa.L = L_.p; sa.diag = diag_.p; sa.mark = mark_.p;
     sa.rowptr = rowptr_.p; sa.rk = rk_asc_.p; sa.rj = rj_asc_.p;
-    sa.parent = parent_.p; sa.z = z_.p; sa.pend = pend_.p; sa.counters = counters_.p;
+    sa.parent = parent_.p; sa.z = z_.p; sa.counters = counters_.p;
     sa.scal_bits = bits_.p; sa.epssol = 1.0e-6;            // _EPSSOL, ldlt.c:28
 
     // eps = epssol*maxv(z,m) is only used when the factorisation met dependent pivots (ldlt.c:446)
     VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_ZMAX, 1);
     VBK_LAUNCH(k_absmax, vec_grid(sym_.m), kVecThreads, 0, stream_, sym_.m, z_.p, bits_.p + S_ZMAX);
-    if (use_flags_) {
-        // per-column completion flags, shared-memory subtract chains (vbk_factor_tiled.cuh)
-        FlagSolveArgs fs;
-        fs.N = N; fs.kL = kL_.p; fs.iL = iL_.p; fs.L = L_.p; fs.diag = diag_.p; fs.mark = mark_.p;
-        fs.rowptr = rowptr_.p; fs.rk = rk_asc_.p; fs.rj = rj_asc_.p; fs.parent = parent_.p;
-        fs.z = z_.p; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
-        fs.nclaim = N;
-        fs.fast = 0;
-        const size_t sm = (size_t)(kSolveThreads / 32) * 128 * sizeof(double);
-        if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
-            rawsolve_window_fast(fs, sa, sm);     // flag kernels below the window, dense sweeps on it
-            return;
-        }
-        VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
-        VBK_LAUNCH(k_fwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
-        VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
-        VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
-        const bool bwd_flags = std::getenv("VBK_BWD") && std::strcmp(std::getenv("VBK_BWD"), "flags") == 0;
-        if (bwd_flags) VBK_LAUNCH(k_bwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
-        else {
-            BwdPipeArgs ba;
-            ba.N = N; ba.nclaim = N; ba.kL = kL_.p; ba.iL = iL_.p; ba.L = L_.p; ba.mark = mark_.p; ba.z = z_.p;
-            ba.done = done_.p; ba.counters = counters_.p; ba.scal_bits = bits_.p; ba.epssol = 1.0e-6;
-            int g = (int)std::max<long long>(1, std::min<long long>((long long)num_sms_ * 6, N));
-#ifdef VBK_EMU
-            g = std::min(g, 3);
-#endif
-            VBK_LAUNCH(k_bwd_pipe, g, kBwdWarps * 32, bwd_pipe_smem_bytes(), stream_, ba);
-        }
-        VBK_CHECK_LAUNCH();
-        stats.kernel_launches += 7;
+    FlagSolveArgs fs;
+    fs.N = N; fs.kL = kL_.p; fs.iL = iL_.p; fs.L = L_.p; fs.diag = diag_.p; fs.mark = mark_.p;
+    fs.rowptr = rowptr_.p; fs.rk = rk_asc_.p; fs.rj = rj_asc_.p; fs.parent = parent_.p;
+    fs.z = z_.p; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
+    fs.nclaim = N;
+    fs.fast = 0;
+    const size_t sm = (size_t)(kSolveThreads / 32) * 128 * sizeof(double);
+    if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
+        rawsolve_window_fast(fs, sa, sm);     // flag kernels below the window, dense sweeps on it
         return;
     }
-    VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, nchild_.p, 0, pend_.p, counters_.p, 2);
-    VBK_LAUNCH(k_fwd_strict, solve_grid_, kSolveThreads, 0, stream_, sa);
+    // forward: per-column completion flags (vbk_flag_solve.cuh); backward: producer/consumer pipeline per column
+    VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
+    VBK_LAUNCH(k_fwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
     VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
-    VBK_LAUNCH(k_reset_pend, vec_grid(N), kVecThreads, 0, stream_, N, (const int*)nullptr, 1, pend_.p, counters_.p, 0);
-    VBK_LAUNCH(k_bwd_strict, solve_grid_, kSolveThreads, 0, stream_, sa);
+    VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
+    {
+        BwdPipeArgs ba;
+        ba.N = N; ba.nclaim = N; ba.kL = kL_.p; ba.iL = iL_.p; ba.L = L_.p; ba.mark = mark_.p; ba.z = z_.p;
+        ba.done = done_.p; ba.counters = counters_.p; ba.scal_bits = bits_.p; ba.epssol = 1.0e-6;
+        int g = (int)std::max<long long>(1, std::min<long long>((long long)num_sms_ * 6, N));
+#ifdef VBK_EMU
+        g = std::min(g, 3);
+#endif
+        VBK_LAUNCH(k_bwd_pipe, g, kBwdWarps * 32, bwd_pipe_smem_bytes(), stream_, ba);
+    }
     VBK_CHECK_LAUNCH();
     stats.kernel_launches += 7;
 }

@@ -12,7 +12,6 @@
 namespace vbk {
 
 enum Mode { kStrict = 0, kFast = 1 };
-struct TiledArgs;
 struct PipeArgs;
 struct FlagSolveArgs;
 struct SolveArgs;
@@ -89,8 +88,8 @@ public:
     KktStats stats;
     // device time of the last numeric-factor kernel (CUDA events on the handle's stream), ms
     float last_factor_kernel_ms();
-    // $VBK_PROF=1: cycles spent per phase by thread 0 of every CTA of the tiled factor kernel since the
-    // last call (8 counters, see vbk_factor_tiled.cuh); zeros when profiling is off
+    // $VBK_PROF=1: cycles spent per phase of the strict factor kernel since the last call (16 counters, see
+    // vbk_strict_factor.cuh); zeros when profiling is off
     void read_phase_profile(unsigned long long out[16]);
     // $VBK_PROF: per-column event times of the last strict factorisation, [N][8] (vbk_strict_factor.cuh)
     void read_trace(long long* out);
@@ -120,8 +119,8 @@ private:
     DevArray<int> iperm_, perm_, kL_, iL_, parent_, nchild_, rowptr_, rk_sig_, rj_sig_, rk_asc_, rj_asc_;
     // numeric
     DevArray<double> L_, diag_;
-    DevArray<int> mark_, pend_, counters_, slotmap_;
-    DevArray<double> gtemp_, scal_;
+    DevArray<int> mark_, counters_;
+    DevArray<double> scal_;
     DevArray<unsigned long long> bits_;
     // solve work vectors
     DevArray<double> z_, xk_, yk_, r_, s_;
@@ -132,48 +131,37 @@ private:
     double* pin_scal_ = nullptr;
     int* pin_cnt_ = nullptr;
 
-    // second-generation strict kernels (vbk_factor_tiled.cuh); $VBK_FACTOR=simple / $VBK_SOLVE=simple
-    // select the first-generation kernels of vbk_kernels.cuh for A/B checks
-    bool use_tiled_ = true, use_flags_ = true;
+    // slice tasks of the numeric factorisation (vbk_symbolic.h) and the strict factor kernel's hand-off state
+    // (vbk_strict_factor.cuh): producer/consumer pipeline per slice task
     DevArray<int> task_col_, task_blk_, task_pos0_, task_cnt_, col_task0_, col_ntask_, winptr_;
-    DevArray<int> col_left_, col_ready_, piv_flag_, piv_keep_, done_;
-    DevArray<double> piv_val_, task_max_;
-    DevArray<long long> trace_;
-    DevArray<unsigned long long> prof_;   // $VBK_PROF: per-phase cycle counters of the tiled factor kernel
-    int tiled_grid_ = 1, tile_doubles_ = 8192, temp_cap_ = 512;
-    size_t tiled_smem_ = 0;
-    void fill_tiled_args(TiledArgs& ta);
-    // third-generation strict factor kernel (vbk_strict_factor.cuh): producer/consumer pipeline per slice task
-    bool use_pipe_ = true;
-    DevArray<int> col_pub_, col_done_;
+    DevArray<int> col_pub_, col_done_, done_;
+    DevArray<double> task_max_;
+    DevArray<long long> trace_;            // $VBK_PROF: per-column event times of the strict factor kernel
+    DevArray<unsigned long long> prof_;    // $VBK_PROF: per-phase cycle counters of the strict factor kernel
     int pipe_grid_ = 1, pipe_warps_ = 8, pipe_stages_ = 8, pipe_cap_ = 32;
     size_t pipe_smem_ = 0;
-    void launch_factor_pipe();
+    void launch_factor_pipe(int ntasks, bool timed);
 
-    // fast mode (vbk_fast.cuh, vbk_kkt_fast.cu): dense scratch for the trailing window
-    bool fast_ready_ = false, light_schur_ = false;
-    int panel_nb_ = 32;
+    // fast mode (vbk_kkt_fast.cu): dense scratch for the trailing window
+    bool fast_ready_ = false;
     DevArray<double> Sw_, P_, dvec_, wmag_, pan_d_, panel_buf_, panel_buf2_;
-    DevArray<int> wmark_, pan_keep_, tri_flags_, tri3_flags_;
-    DevArray<int> sp_end_, sp_lvlcol_;          // fast sparse columns (vbk_fast6.cuh): sparse prefix ends, columns by level
+    DevArray<int> wmark_, pan_keep_, tri3_flags_;
+    DevArray<int> sp_end_, sp_lvlcol_;          // fast sparse columns (vbk_sparse_level.cuh): sparse prefix ends, columns by level
     std::vector<int> sp_lvlptr_;
     int sp_cap_ = 2, sp_cap_heavy_ = 2;
     int sparse_tuned_ = 0;                      // 0, 1: measuring the two sparse-column paths; 2: decided
     float sparse_ms_[2] = {0.f, 0.f};           // [0] task kernel, [1] level kernels
     cudaEvent_t ev_sp0_ = nullptr, ev_sp1_ = nullptr;
-    DevArray<double> tinv_, tri_racc_;          // inverted diagonal blocks + slice accumulators of the 128-row sweeps (vbk_fast5.cuh)
+    DevArray<double> tinv_, tri_racc_;          // inverted diagonal blocks + slice accumulators of the 128-row sweeps (vbk_window_solve.cuh)
     DevArray<unsigned long long> panel_prof_;
     // look-ahead: the bulk of a panel's trailing update runs on a second stream while the next panel is factorised
-    cudaStream_t stream2_ = 0, stream3_ = 0;
-    cudaEvent_t ev_diag_[2] = {nullptr, nullptr}, ev_rowsa_[2] = {nullptr, nullptr}, ev_rowsb_[2] = {nullptr, nullptr}, ev_stripb_[2] = {nullptr, nullptr};
+    cudaStream_t stream2_ = 0;
     cudaEvent_t ev_rows_[2] = {nullptr, nullptr}, ev_updb_[2] = {nullptr, nullptr};
     void prepare_fast();
-    void factor_window_fast(TiledArgs& ta);
+    void factor_window_fast();
     void rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_smem);
-    int factor_grid_ = 1, solve_grid_ = 1;
+    int solve_grid_ = 1;
     cudaEvent_t ev_f0_ = nullptr, ev_f1_ = nullptr;
-    size_t factor_smem_ = 0;
-    int smem_slots_ = 4096;
 };
 
 }  // namespace vbk

@@ -1,6 +1,8 @@
-// vbk_kkt_fast.cu -- host orchestration of FAST mode (kernels in vbk_fast.cuh).
+// vbk_kkt_fast.cu -- host orchestration of FAST mode (kernels in vbk_sparse_level.cuh, vbk_schur.cuh,
+// vbk_dense_panel.cuh, vbk_dense_update.cuh, vbk_window_solve.cuh).
 #include "vbk_kkt.h"
-#include "vbk_fast6.cuh"
+#include "vbk_strict_factor.cuh"
+#include "vbk_schur.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -15,8 +17,6 @@ void Kkt::prepare_fast()
     fast_ready_ = false;
     sparse_tuned_ = 0;
     if (W <= 0) return;
-    if (const char* e = std::getenv("VBK_PANEL")) panel_nb_ = std::max(1, std::min(kPanelMax, std::atoi(e)));
-    else panel_nb_ = kPanelMax;
     Sw_.alloc((size_t)W * W);
     P_.alloc((size_t)2 * W * kOuterPanel);          // two panels of L21*D: the look-ahead keeps two updates in flight
     dvec_.alloc(W); wmag_.alloc(W); wmark_.alloc(W);
@@ -24,28 +24,24 @@ void Kkt::prepare_fast()
 #ifndef VBK_EMU
     panel_buf2_.alloc((size_t)2 * kPanelBuf2Doubles);
 #endif
-    tri_flags_.alloc((size_t)(W + 31) / 32 + 1);
     {
         const int npan = (W + kTriPW - 1) / kTriPW;
         tinv_.alloc((size_t)npan * kTriPW * kTriPW);
-        tri_racc_.alloc((size_t)npan * kTriPW);
+        tri_racc_.alloc((size_t)npan * kTriPW * kTriSplit);
         tri3_flags_.alloc((size_t)2 * npan + 1);
     }
     {
-        // how many sparse-column contributions do the window rows see?  Few => light Schur kernel.
-        long long nsc = 0;
+        // end of the sparse prefix (columns j < T) of every window row's ascending list
         std::vector<int> spend((size_t)W);
         for (int i = T; i < N; ++i) {
             const int* b = sym_.rj_asc.data() + sym_.rowptr[i];
             const int* e = sym_.rj_asc.data() + sym_.rowptr[i + 1];
-            const long long cnt = std::lower_bound(b, e, T) - b;
-            nsc += cnt;
-            spend[(size_t)(i - T)] = sym_.rowptr[i] + (int)cnt;
+            spend[(size_t)(i - T)] = sym_.rowptr[i] + (int)(std::lower_bound(b, e, T) - b);
         }
         sp_end_.upload(spend, stream_);
         // etree levels of the sparse columns (parent restricted to j < T): every level is one launch of
-        // k_sparse_level for its light columns and one of k_sparse_level_heavy for the heavy ones (vbk_fast6.cuh).
-        // weight of a column = entries its contributors' tails apply to it
+        // k_sparse_level for its light columns and one of k_sparse_level_heavy for the heavy ones
+        // (vbk_sparse_level.cuh).  weight of a column = entries its contributors' tails apply to it
         std::vector<int> lev((size_t)std::max(T, 1), 0);
         std::vector<char> heavy((size_t)std::max(T, 1), 0);
         int nlev = 0, cap_l = 1, cap_h = 1;
@@ -70,38 +66,23 @@ void Kkt::prepare_fast()
         sp_lvlcol_.upload(cols, stream_);
         sp_cap_ = (cap_l + 1) & ~1;
         sp_cap_heavy_ = (cap_h + 1) & ~1;
-        const char* es = std::getenv("VBK_SCHUR");
-        light_schur_ = es ? (std::string(es) == "light") : (nsc <= 128LL * W);
     }
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_schur_window2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_window_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTinvSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_window_tri3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriV3Smem));
-#ifndef VBK_EMU
-    // kernels are `static` in the headers: this translation unit launches its own copy
-    VBK_CUDA(cudaFuncSetAttribute(k_factor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
-    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_rt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 2 * kPanelMax * kUpdTD)));
-    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdPipeSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 128>::kSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 64>::kSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64, 64>::kSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelDiagSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_panel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsSmem));
-    VBK_CUDA(cudaFuncSetAttribute(k_panel_rows_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsMSmem));
-#endif
 #ifndef VBK_EMU
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<128, 64>::kSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_dense_update_m<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UpdMma<64, 64>::kSmem));
+    VBK_CUDA(cudaFuncSetAttribute(k_panel_rows_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelRowsMSmem));
     if (!stream2_) {
         VBK_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
-        VBK_CUDA(cudaStreamCreateWithFlags(&stream3_, cudaStreamNonBlocking));
         for (int u = 0; u < 2; ++u) {
-            VBK_CUDA(cudaEventCreateWithFlags(&ev_diag_[u], cudaEventDisableTiming));
-            VBK_CUDA(cudaEventCreateWithFlags(&ev_rowsa_[u], cudaEventDisableTiming));
-            VBK_CUDA(cudaEventCreateWithFlags(&ev_rowsb_[u], cudaEventDisableTiming));
-            VBK_CUDA(cudaEventCreateWithFlags(&ev_stripb_[u], cudaEventDisableTiming));
             VBK_CUDA(cudaEventCreateWithFlags(&ev_rows_[u], cudaEventDisableTiming));
             VBK_CUDA(cudaEventCreateWithFlags(&ev_updb_[u], cudaEventDisableTiming));
         }
@@ -110,26 +91,24 @@ void Kkt::prepare_fast()
     fast_ready_ = true;
 }
 
-// Numeric factorisation in fast mode.  `ta` arrives filled for a plain (phase 0) launch.
-void Kkt::factor_window_fast(TiledArgs& ta)
+// Numeric factorisation in fast mode: sparse columns (bit-exact), Schur assembly, dense window, solve operands.
+void Kkt::factor_window_fast()
 {
     const int N = sym_.N, T = sym_.dense_start, W = N - T;
     const int sparse_tasks = sym_.col_task0[T];
-
-    // 1. columns j < T: the strict task kernel (bit-exact for these columns, dependent-pivot rule
-    //    included).  k_tiled_reset has already run.
     int launches = 2;
-    // throughput kernels of vbk_fast6.cuh unless $VBK_SPARSE=strict / $VBK_SCHUR=light|heavy ask for the first generation
+
+    // 1. columns j < T keep the reference's arithmetic.  Two kernels produce the same bits for them -- the strict slice
+    //    tasks (vbk_strict_factor.cuh) and one launch per elimination-tree level (vbk_sparse_level.cuh) -- so the choice
+    //    is a pure timing question and is made by measurement: the first factorisation of a handle runs the task
+    //    kernel, the second the level kernels (CUDA events around this phase, one synchronisation each), every later
+    //    one whichever was faster.  Deep, thin trees (pilot87: 99 levels) favour the task kernel's column-level
+    //    dataflow, shallow wide ones (dfl001, multicommodity) the level kernels.  $VBK_SPARSE=strict|level pins it.
     const char* esp = std::getenv("VBK_SPARSE");
     const size_t sp_smem = (size_t)kSpWarps * sp_cap_ * (2 * sizeof(double) + sizeof(int));
     const size_t sph_smem = sizeof(double) * ((size_t)2 * sp_cap_heavy_ + 2 * kSpHeavyBatch + kSpHeavyThreads)
                             + sizeof(int) * ((size_t)sp_cap_heavy_ + W + 2 * kSpHeavyBatch + 2);
     const bool levels_ok = sp_smem <= (size_t)smem_optin_ && sph_smem <= (size_t)smem_optin_;
-    // Both paths produce the same bits for the sparse columns, so the choice is a pure timing question and is made by
-    // measurement: the first factorisation of a handle runs the task kernel, the second the level kernels (CUDA
-    // events around this phase, one synchronisation each), every later one whichever was faster.  Deep, thin trees
-    // (pilot87: 99 levels) favour the task kernel's column-level dataflow, shallow wide ones (dfl001, multicommodity)
-    // the level kernels.  $VBK_SPARSE=strict|level pins the choice.
     bool sparse_levels = levels_ok;
     int tune_slot = -1;
     if (esp && std::string(esp) == "strict") sparse_levels = false;
@@ -142,15 +121,13 @@ void Kkt::factor_window_fast(TiledArgs& ta)
         if (!ev_sp0_) { VBK_CUDA(cudaEventCreate(&ev_sp0_)); VBK_CUDA(cudaEventCreate(&ev_sp1_)); }
         VBK_CUDA(cudaEventRecord(ev_sp0_, stream_));
     }
-    if (sparse_tasks > 0 && !sparse_levels) {
-        ta.phase = 0; ta.task_base = 0; ta.ntasks = sparse_tasks;
-        VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(sparse_tasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
-    }
+    if (sparse_tasks > 0 && !sparse_levels) launch_factor_pipe(sparse_tasks, false);
+    else VBK_LAUNCH(k_pipe_reset, vec_grid(N), kVecThreads, 0, stream_, N, col_pub_.p, col_done_.p, counters_.p);   // ndep = 0
     if (T > 0 && sparse_levels) {
         SparseLevelArgs sl;
         sl.n_ld = sym_.n; sl.T = T; sl.W = W; sl.kL = kL_.p; sl.iL = iL_.p; sl.L = L_.p; sl.diag = diag_.p; sl.mark = mark_.p;
         sl.perm = perm_.p; sl.rowptr = rowptr_.p; sl.rk = rk_sig_.p; sl.rj = rj_sig_.p; sl.counters = counters_.p;
-        sl.scal_bits = bits_.p; sl.epsnum = ta.epsnum;
+        sl.scal_bits = bits_.p; sl.epsnum = 0.0;                     // _EPSNUM, ldlt.c:29
         for (size_t l = 0; l + 2 < sp_lvlptr_.size(); l += 2) {
             const int nl = sp_lvlptr_[l + 1] - sp_lvlptr_[l], nh = sp_lvlptr_[l + 2] - sp_lvlptr_[l + 1];
             if (nl > 0) {
@@ -177,27 +154,20 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     // 2. Schur complement of the sparse columns on the window, written densely; no dependencies.
     //    Entries outside the fill pattern are never written: start from zero.
     VBK_CUDA(cudaMemsetAsync(Sw_.p, 0, sizeof(double) * (size_t)W * W, stream_));
-    const char* esc = std::getenv("VBK_SCHUR");
-    const size_t sc2_smem = sizeof(double) * ((size_t)W + 2 * kSchur2Batch) + sizeof(int) * 2 * kSchur2Batch;
-    const bool schur2 = !esc && sc2_smem <= (size_t)smem_optin_;
-    if (schur2) {
+    {
+        const size_t sc2_smem = sizeof(double) * ((size_t)W + 2 * kSchur2Batch) + sizeof(int) * 2 * kSchur2Batch;
+        if (sc2_smem > (size_t)smem_optin_) {
+            std::fprintf(stderr, "vbkkt: dense window of %d columns exceeds the Schur assembly's shared memory\n", W);
+            std::exit(1);
+        }
         Schur2Args sc;
         sc.N = N; sc.T = T; sc.ld = W; sc.cap = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
         sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.spend = sp_end_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;
         VBK_LAUNCH(k_schur_window2, std::min(W, num_sms_ * 6), kSchur2Threads, sc2_smem, stream_, sc);
-    } else if (light_schur_) {
-        SchurArgs sc;
-        sc.N = N; sc.T = T; sc.ld = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
-        sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;
-        VBK_LAUNCH(k_schur_window, std::min(W, num_sms_ * 8), kDenseThreads, 0, stream_, sc);
-    } else {
-        VBK_LAUNCH(k_zero_counter, 1, 32, 0, stream_, counters_.p, (int)C_NEXT);
-        ta.phase = 2; ta.task_base = sparse_tasks; ta.ntasks = sym_.ntasks() - sparse_tasks;
-        ta.T = T; ta.ldw = W; ta.Sw = Sw_.p; ta.wmag = wmag_.p;
-        VBK_LAUNCH(k_factor_tiled, std::min(tiled_grid_, std::max(ta.ntasks, 1)), kTiledThreads, tiled_smem_, stream_, ta);
     }
 
-    // 3. blocked right-looking dense LDL^T of the window
+    // 3. blocked right-looking dense LDL^T of the window: 128-column panels (vbk_dense_panel.cuh) -- diagonal block,
+    //    rows below, rank-128 trailing update on the FP64 tensor path (vbk_dense_update.cuh)
     DenseArgs da;
     da.W = W; da.ld = W; da.S = Sw_.p; da.P = P_.p; da.dvec = dvec_.p; da.wmag = wmag_.p; da.wmark = wmark_.p;
     da.pan_d = pan_d_.p; da.pan_keep = pan_keep_.p; da.PB = panel_buf_.p; da.prof = nullptr; da.perm = perm_.p; da.T = T; da.n_ld = sym_.n;
@@ -214,165 +184,53 @@ void Kkt::factor_window_fast(TiledArgs& ta)
     // pivoting"; iterative refinement absorbs the perturbation).  $VBK_PIVOT_STATIC=0 restores the literal rule.
     da.piv_scale = 1.4901161193847656e-08;
     if (const char* e = std::getenv("VBK_PIVOT_STATIC")) da.piv_scale = std::atof(e);
-    const size_t sm_diag = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax + kDenseThreads) + sizeof(int) * kPanelMax;
-    const size_t sm_trsm = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;
-    const size_t sm_upd = sizeof(double) * 2 * kPanelMax * kTileDim;
-    const size_t sm_upd_rt = sizeof(double) * 2 * kPanelMax * kUpdTD;
-    const char* eu = std::getenv("VBK_UPDATE");
-    const bool simple_update = eu && std::string(eu) == "simple";
-    const char* ed = std::getenv("VBK_DENSE");
-    const bool dense_v1 = ed && std::string(ed) == "v1";
-    const bool dense_v2 = ed && std::string(ed) == "v2";
-    if (!dense_v1 && !dense_v2) {
-        // 128-column panels (vbk_fast3.cuh): diagonal block, rows below, rank-128 trailing update
+    {
         static const bool prof_on = std::getenv("VBK_PROF") != nullptr;
         if (prof_on) {
             panel_prof_.alloc(16);
             VBK_CUDA(cudaMemsetAsync(panel_prof_.p, 0, 16 * sizeof(unsigned long long), stream_));
             da.prof = panel_prof_.p;
         }
-        const char* el = std::getenv("VBK_LOOKAHEAD");
-#ifdef VBK_EMU
-        const bool lookahead = !(el && el[0] == '0');             // same split of the update, one (emulated) stream
-        cudaStream_t sB = stream_;
-#else
-        const bool lookahead = !(el && el[0] == '0') && stream2_ != nullptr;
-        cudaStream_t sB = stream2_;
-#endif
         // Look-ahead of depth one.  Panel k's rank-128 update is split: the columns of panel k+1 ("A part", few
         // tiles) stay on the main stream, everything to the right of them ("B part", nearly all the flops) goes to
         // a second stream and overlaps with the factorisation of panel k+1, which is a latency-bound chain on one or
         // a few SMs.  Hazards: B_k reads P_k and the columns of panel k and writes strictly-lower entries right of
         // panel k+1 only -- nothing panel k+1's kernels touch (they write their own columns, the other P buffer and
         // diagonal entries); A_{k+1} and rows_{k+2} (which reuses P_k's buffer) wait for B_k.
-        // rank-128 trailing update (vbk_fast4.cuh): DMMA tiles fed by a cp.async ring; $VBK_UPDATE=m128 / p select 128 x 128 DMMA tiles / the
-        // DFMA version of the same pipeline, $VBK_UPDATE=k the unpipelined second-generation kernel (A/B runs)
 #ifdef VBK_EMU
+        cudaStream_t sB = stream_;               // same split of the update, one (emulated) stream
         auto launch_update = [&](int tiles, cudaStream_t st, const DenseArgs& d) {
-            VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, st, d);
+            VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sizeof(double) * 2 * kPanelMax * kUpdTD, st, d);
         };
 #else
-        const std::string upd = eu ? eu : "";
+        cudaStream_t sB = stream2_;
         auto launch_update = [&](int tiles, cudaStream_t st, const DenseArgs& d) {
-            if (upd == "k") VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, st, d);
-            else if (upd == "p") VBK_LAUNCH(k_dense_update_p, dim3(tiles, tiles), 256, kUpdPipeSmem, st, d);
-            else if (upd == "m128") VBK_LAUNCH((k_dense_update_m<128, 128>), dim3(tiles, tiles), (UpdMma<128, 128>::kThreads), (UpdMma<128, 128>::kSmem), st, d);
-            else VBK_LAUNCH((k_dense_update_m<128, 64>), dim3(2 * tiles, tiles), (UpdMma<128, 64>::kThreads), (UpdMma<128, 64>::kSmem), st, d);
+            VBK_LAUNCH((k_dense_update_m<128, 64>), dim3(2 * tiles, tiles), (UpdMma<128, 64>::kThreads), (UpdMma<128, 64>::kSmem), st, d);
         };
-#endif
-#ifndef VBK_EMU
-        const bool rows_mma = !(std::getenv("VBK_ROWS") && std::string(std::getenv("VBK_ROWS")) == "dfma");
-        da.PB2 = rows_mma ? panel_buf2_.p : nullptr;
-#endif
-#ifndef VBK_EMU
-        // Split look-ahead.  Only the 128 x 128 diagonal tile of panel k+1 stands between two panel factorisations:
-        // it needs the first 128 rows of rows_k and one tile of the strip update.  Everything else of rows_k and of the
-        // strip runs on a third stream while panel k+1 is being factorised (41 us of work under a 58 us kernel on
-        // dfl001), so the dependent chain per panel is diag -> 8 slabs of rows -> 4 tiles -> diag.
-        //   main:  diag_k, rowsA_k (waits stripB_{k-1}), stripA_k (waits B_{k-1})
-        //   sC:    rowsB_k (waits diag_k), stripB_k (waits rowsA_k, B_{k-1})
-        //   sB:    B_k (waits rowsA_k, rowsB_k)
-        // Buffers written by diag_{k+1} / rows_{k+1} while sC still reads: P and the packed operand buffer alternate.
-        // Measured on dfl001 (profiles/r01_summary.md): results identical, KKT step 7.03 ms with the split against 6.80 ms
-        // without -- the four cross-stream event hand-offs per panel cost more than the 41 us they take off the chain.
-        // Kept behind $VBK_SPLIT=1 (a single-kernel panel chain with in-kernel flags is the way to collect this).
-        const bool split = lookahead && rows_mma && kStripTD == 64 && stream3_ != nullptr
-                           && std::getenv("VBK_SPLIT") && std::getenv("VBK_SPLIT")[0] == '1';
-        if (split) {
-            cudaStream_t sC = stream3_;
-            int k = 0, prev_b = -1, prev_sb = -1;
-            for (int P0 = 0; P0 < W; P0 += kPanelW, ++k) {
-                const int u = k & 1;
-                da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0; da.rskip = 0; da.slab_lo = 0; da.slab_hi = 0x7fffffff;
-                da.P = P_.p + (size_t)u * W * kOuterPanel;
-                da.PB2 = panel_buf2_.p + (size_t)u * kPanelBuf2Doubles;
-                VBK_LAUNCH(k_panel_diag, 1, kDiagThreads, kPanelDiagSmem, stream_, da);
-                ++launches;
-                const int below = W - P0 - da.nb;
-                if (below <= 0) continue;
-                VBK_CUDA(cudaEventRecord(ev_diag_[u], stream_));
-                const int kend = P0 + da.nb;
-                const int nslabs = (below + 15) / 16, slabsA = std::min(nslabs, kPanelW / 16);
-                // rows: part A on the main stream, part B on sC
-                if (prev_sb >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_stripb_[prev_sb & 1], 0));
-                DenseArgs ra = da; ra.slab_lo = 0; ra.slab_hi = slabsA;
-                VBK_LAUNCH(k_panel_rows_m, std::max(1, (slabsA + kRowsMWarps - 1) / kRowsMWarps), kRowsMWarps * 32, kPanelRowsMSmem, stream_, ra);
-                VBK_CUDA(cudaEventRecord(ev_rowsa_[u], stream_));
-                ++launches;
-                const bool haveB = nslabs > slabsA;
-                if (haveB) {
-                    VBK_CUDA(cudaStreamWaitEvent(sC, ev_diag_[u], 0));
-                    DenseArgs rb = da; rb.slab_lo = slabsA; rb.slab_hi = 0x7fffffff;
-                    const int gm = std::min((nslabs - slabsA + kRowsMWarps - 1) / kRowsMWarps, num_sms_ * 2);
-                    VBK_LAUNCH(k_panel_rows_m, gm, kRowsMWarps * 32, kPanelRowsMSmem, sC, rb);
-                    VBK_CUDA(cudaEventRecord(ev_rowsb_[u], sC));
-                    ++launches;
-                }
-                da.kcol0 = P0; da.klen = da.nb;
-                // bulk update B_k on sB
-                const int rest = W - (kend + kPanelW);
-                if (rest > 0) {
-                    VBK_CUDA(cudaStreamWaitEvent(sB, ev_rowsa_[u], 0));
-                    if (haveB) VBK_CUDA(cudaStreamWaitEvent(sB, ev_rowsb_[u], 0));
-                    DenseArgs db = da;
-                    db.rbase = kend + kPanelW; db.cmax = W;
-                    launch_update((rest + kUpdTD - 1) / kUpdTD, sB, db);
-                    VBK_CUDA(cudaEventRecord(ev_updb_[u], sB));
-                    ++launches;
-                }
-                // strip: diagonal tile of panel k+1 on the main stream, the rows below it on sC
-                if (prev_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[prev_b & 1], 0));
-                DenseArgs sa = da;
-                sa.rbase = kend; sa.cmax = std::min(kend + kPanelW, W); sa.rskip = 0;
-                const int tc = (sa.cmax - kend + kStripTD - 1) / kStripTD;
-                const int trA = std::min((below + kStripTD - 1) / kStripTD, kPanelW / kStripTD);
-                VBK_LAUNCH((k_dense_update_m<64, 64>), dim3(tc, trA), (UpdMma<64, 64>::kThreads), (UpdMma<64, 64>::kSmem), stream_, sa);
-                ++launches;
-                if (below > kPanelW) {
-                    VBK_CUDA(cudaStreamWaitEvent(sC, ev_rowsa_[u], 0));
-                    if (prev_b >= 0) VBK_CUDA(cudaStreamWaitEvent(sC, ev_updb_[prev_b & 1], 0));
-                    DenseArgs sb2 = sa; sb2.rskip = kPanelW;
-                    const int trB = (below - kPanelW + kStripTD - 1) / kStripTD;
-                    VBK_LAUNCH((k_dense_update_m<64, 64>), dim3(tc, trB), (UpdMma<64, 64>::kThreads), (UpdMma<64, 64>::kSmem), sC, sb2);
-                    VBK_CUDA(cudaEventRecord(ev_stripb_[u], sC));
-                    prev_sb = k;
-                    ++launches;
-                } else prev_sb = -1;
-                prev_b = rest > 0 ? k : -1;
-            }
-            if (prev_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[prev_b & 1], 0));
-            if (prev_sb >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_stripb_[prev_sb & 1], 0));
-            da.rskip = 0; da.slab_lo = 0; da.slab_hi = 0x7fffffff;
-        } else {
+        da.PB2 = panel_buf2_.p;
 #endif
         int k = 0, last_b = -1;
         for (int P0 = 0; P0 < W; P0 += kPanelW, ++k) {
             da.p = P0; da.nb = std::min(kPanelW, W - P0); da.pcol0 = 0;
-            da.P = P_.p + (size_t)(lookahead ? (k & 1) : 0) * W * kOuterPanel;
+            da.P = P_.p + (size_t)(k & 1) * W * kOuterPanel;
             VBK_LAUNCH(k_panel_diag, 1, kDiagThreads, kPanelDiagSmem, stream_, da);
             ++launches;
             const int below = W - P0 - da.nb;
             if (below <= 0) continue;
 #ifndef VBK_EMU
-            if (rows_mma) {
+            {
                 const int gm = std::min((below + 16 * kRowsMWarps - 1) / (16 * kRowsMWarps), num_sms_ * 2);
                 VBK_LAUNCH(k_panel_rows_m, gm, kRowsMWarps * 32, kPanelRowsMSmem, stream_, da);
-            } else
-#endif
-            {
-            const int g = std::min((below + kRowsPerCta - 1) / kRowsPerCta, num_sms_ * 4);
-            VBK_LAUNCH(k_panel_rows, g, kRowThreads, kPanelRowsSmem, stream_, da);
             }
+#else
+            {
+                const int g = std::min((below + kRowsPerCta - 1) / kRowsPerCta, num_sms_ * 4);
+                VBK_LAUNCH(k_panel_rows, g, kRowThreads, kPanelRowsSmem, stream_, da);
+            }
+#endif
             ++launches;
             const int kend = P0 + da.nb;
             da.kcol0 = P0; da.klen = da.nb;
-            if (!lookahead) {
-                da.rbase = kend; da.cmax = W;
-                const int tiles = (below + kUpdTD - 1) / kUpdTD;
-                launch_update(tiles, stream_, da);
-                ++launches;
-                continue;
-            }
             const int rest = W - (kend + kPanelW);                  // columns right of panel k+1
             if (rest > 0) {                                         // B part on the second stream
 #ifndef VBK_EMU
@@ -381,8 +239,7 @@ void Kkt::factor_window_fast(TiledArgs& ta)
 #endif
                 DenseArgs db = da;
                 db.rbase = kend + kPanelW; db.cmax = W;
-                const int tiles = (rest + kUpdTD - 1) / kUpdTD;
-                launch_update(tiles, sB, db);
+                launch_update((rest + kUpdTD - 1) / kUpdTD, sB, db);
 #ifndef VBK_EMU
                 VBK_CUDA(cudaEventRecord(ev_updb_[k & 1], sB));
 #endif
@@ -396,17 +253,14 @@ void Kkt::factor_window_fast(TiledArgs& ta)
             da.rbase = kend; da.cmax = std::min(kend + kPanelW, W);
             const int tr = (below + kStripTD - 1) / kStripTD, tc = (da.cmax - kend + kStripTD - 1) / kStripTD;
 #ifndef VBK_EMU
-            static const bool strip_dfma = std::getenv("VBK_STRIP") && std::string(std::getenv("VBK_STRIP")) == "dfma";
-            if (!strip_dfma && kStripTD == 64)
-                VBK_LAUNCH((k_dense_update_m<64, 64>), dim3(tc, tr), (UpdMma<64, 64>::kThreads), (UpdMma<64, 64>::kSmem), stream_, da);
-            else
-#endif
+            VBK_LAUNCH((k_dense_update_m<64, 64>), dim3(tc, tr), (UpdMma<64, 64>::kThreads), (UpdMma<64, 64>::kSmem), stream_, da);
+#else
             VBK_LAUNCH(k_dense_update_strip, dim3(tc, tr), kStripThreads, sizeof(double) * 2 * kPanelMax * kStripTD, stream_, da);
+#endif
             ++launches;
         }
 #ifndef VBK_EMU
-        if (lookahead && last_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[last_b & 1], 0));
-        }
+        if (last_b >= 0) VBK_CUDA(cudaStreamWaitEvent(stream_, ev_updb_[last_b & 1], 0));
 #endif
     }
     if (da.prof) {
@@ -417,63 +271,13 @@ void Kkt::factor_window_fast(TiledArgs& ta)
                      "(%llu sub-blocks, %llu repeated with the full pivot rule) block trsm %llu, block update %llu, store %llu | rows: panel fetch %llu, row loads %llu, rank update %llu, "
                      "stages %llu, stores %llu\n", (W + kPanelW - 1) / kPanelW, h[0], h[1], h[14], h[15], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
     }
-    if (dense_v2) {
-        // two-level blocking (vbk_fast2.cuh): inner panels of panel_nb_ columns, one rank-(outer) update of
-        // the trailing matrix per outer panel
-        const size_t sm_diag_w = sizeof(double) * (kPanelMax * (kPanelMax + 1) + kPanelMax) + sizeof(int) * kPanelMax;
-        const int outer = std::max(panel_nb_, (kOuterPanel / kPanelMax) * panel_nb_);
-        for (int P0 = 0; P0 < W; P0 += outer) {
-            const int kend = std::min(P0 + outer, W);
-            for (int p = P0; p < kend; p += panel_nb_) {
-                da.p = p; da.nb = std::min(panel_nb_, kend - p);
-                da.pcol0 = p - P0;
-                VBK_LAUNCH(k_dense_diag_w, 1, 32, sm_diag_w, stream_, da);
-                ++launches;
-                const int below = W - p - da.nb;
-                if (below <= 0) continue;
-                const int g = std::min((below + kDenseThreads - 1) / kDenseThreads, num_sms_ * 4);
-                VBK_LAUNCH(k_dense_trsm_u, g, kDenseThreads, sm_trsm, stream_, da);
-                ++launches;
-                if (kend - (p + da.nb) > 0) {        // the rest of the outer panel's own strip
-                    da.kcol0 = p; da.klen = da.nb; da.rbase = p + da.nb; da.cmax = kend;
-                    const int tr = (W - da.rbase + kUpdTD - 1) / kUpdTD, tc = (kend - da.rbase + kUpdTD - 1) / kUpdTD;
-                    VBK_LAUNCH(k_dense_update_k, dim3(tc, tr), kUpdThreads, sm_upd_rt, stream_, da);
-                    ++launches;
-                }
-            }
-            if (W - kend > 0) {                        // trailing matrix: one rank-(kend-P0) update
-                da.kcol0 = P0; da.klen = kend - P0; da.pcol0 = 0; da.rbase = kend; da.cmax = W;
-                const int tiles = (W - kend + kUpdTD - 1) / kUpdTD;
-                VBK_LAUNCH(k_dense_update_k, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
-                ++launches;
-            }
-        }
-    }
-    for (int p = 0; dense_v1 && p < W; p += panel_nb_) {
-        da.p = p; da.nb = std::min(panel_nb_, W - p);
-        VBK_LAUNCH(k_dense_diag, 1, kDenseThreads, sm_diag, stream_, da);
-        ++launches;
-        const int below = W - p - da.nb;
-        if (below > 0) {
-            const int g = std::min((below + kDenseThreads - 1) / kDenseThreads, num_sms_ * 4);
-            VBK_LAUNCH(k_dense_trsm, g, kDenseThreads, sm_trsm, stream_, da);
-            if (simple_update) {
-                const int tiles = (below + kTileDim - 1) / kTileDim;
-                VBK_LAUNCH(k_dense_update, dim3(tiles, tiles), kDenseThreads, sm_upd, stream_, da);
-            } else {
-                const int tiles = (below + kUpdTD - 1) / kUpdTD;
-                VBK_LAUNCH(k_dense_update_rt, dim3(tiles, tiles), kUpdThreads, sm_upd_rt, stream_, da);
-            }
-            launches += 2;
-        }
-    }
     // 4. mirror L into the upper triangle (the backward sweep then reads rows, like the forward one)
     {
         const int nt32 = (W + 31) / 32;
         VBK_LAUNCH(k_window_mirror, dim3(nt32, nt32), kVecThreads, 32 * 33 * sizeof(double), stream_, W, W, Sw_.p);
         ++launches;
     }
-    // 4b. inverses of the 128 x 128 diagonal blocks for the triangular sweeps (vbk_fast5.cuh)
+    // 4b. inverses of the 128 x 128 diagonal blocks for the triangular sweeps (vbk_window_solve.cuh)
     VBK_LAUNCH(k_window_tinv, (W + kTriPW - 1) / kTriPW, kTriPW, kTinvSmem, stream_, W, W, Sw_.p, tinv_.p);
     ++launches;
     // 5. back into the packed storage the strict-layout consumers (tests, get_factor) read
@@ -489,28 +293,20 @@ void Kkt::factor_window_fast(TiledArgs& ta)
 
 void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_smem)
 {
-    const int N = sym_.N, T = sym_.dense_start;
+    const int N = sym_.N, T = sym_.dense_start, W = N - T;
     WindowSolveArgs wa;
-    wa.N = N; wa.T = T; wa.ld = N - T; wa.S = Sw_.p; wa.kL = kL_.p; wa.L = L_.p; wa.mark = mark_.p;
+    wa.N = N; wa.T = T; wa.ld = W; wa.S = Sw_.p; wa.kL = kL_.p; wa.L = L_.p; wa.mark = mark_.p;
     wa.rowptr = rowptr_.p; wa.rk = rk_asc_.p; wa.rj = rj_asc_.p; wa.z = z_.p; wa.spend = sp_end_.p;
     wa.counters = counters_.p; wa.scal_bits = bits_.p; wa.epssol = 1.0e-6;
     fs.nclaim = T;
     fs.fast = 1;
     const int gsolve = std::max(1, std::min(solve_grid_, (T + 3) / 4));
-    const int ggather = std::max(1, std::min(num_sms_ * 4, ((N - T) * 32 + kSolveThreads - 1) / kSolveThreads));
+    const int ggather = std::max(1, std::min(num_sms_ * 4, (W * 32 + kSolveThreads - 1) / kSolveThreads));
 
     VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
     if (T > 0) VBK_LAUNCH(k_fwd_flags, gsolve, kSolveThreads, flag_smem, stream_, fs);
     VBK_LAUNCH(k_window_gather, ggather, kSolveThreads, 0, stream_, wa);
-    const char* ew = std::getenv("VBK_WSOLVE");
-    const bool wsolve_v1 = ew && std::string(ew) == "v1";
-    TriArgs tr;
-    const int W = N - T;
-    tr.W = W; tr.ld = W; tr.npanels = (W + 31) / 32; tr.S = Sw_.p; tr.z = z_.p + T; tr.mark = mark_.p + T;
-    tr.flags = tri_flags_.p; tr.counters = counters_.p; tr.scal_bits = bits_.p; tr.epssol = 1.0e-6;
-    const int gtri = std::max(1, std::min(tr.npanels, num_sms_));
-    const size_t sm_tri = (size_t)(kTriThreads / 32) * 32 * sizeof(double) + 16;   // + the claim slot
-    const bool wsolve_v2 = ew && std::string(ew) == "v2";
+    // window: 128-row panels with inverted diagonal blocks (vbk_window_solve.cuh)
     Tri3Args t3;
     t3.W = W; t3.ld = W; t3.npan = (W + kTriPW - 1) / kTriPW; t3.S = Sw_.p; t3.Tinv = tinv_.p; t3.z = z_.p + T;
     t3.mark = mark_.p + T; t3.racc = tri_racc_.p; t3.flags = tri3_flags_.p; t3.counters = counters_.p;
@@ -518,25 +314,13 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     const int g3 = std::max(1, std::min(t3.npan * kTriSplit, num_sms_));
     auto sweep3 = [&](int dir) {
         VBK_CUDA(cudaMemsetAsync(tri3_flags_.p, 0, sizeof(int) * (size_t)(2 * t3.npan + 1), stream_));
-        VBK_CUDA(cudaMemsetAsync(tri_racc_.p, 0, sizeof(double) * (size_t)t3.npan * kTriPW, stream_));
+        VBK_CUDA(cudaMemsetAsync(tri_racc_.p, 0, sizeof(double) * (size_t)t3.npan * kTriPW * kTriSplit, stream_));
         t3.dir = dir;
         VBK_LAUNCH(k_window_tri3, g3, kTriV3Threads, kTriV3Smem, stream_, t3);
     };
-    if (wsolve_v1) VBK_LAUNCH(k_window_fwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
-    else if (!wsolve_v2) sweep3(0);
-    else {
-        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)(tr.npanels + 1), stream_));
-        tr.dir = 0;
-        VBK_LAUNCH(k_window_tri, gtri, kTriThreads, sm_tri, stream_, tr);
-    }
+    sweep3(0);
     VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
-    if (wsolve_v1) VBK_LAUNCH(k_window_bwd, 1, kDenseThreads, 32 * sizeof(double), stream_, wa);
-    else if (!wsolve_v2) sweep3(1);
-    else {
-        VBK_CUDA(cudaMemsetAsync(tri_flags_.p, 0, sizeof(int) * (size_t)(tr.npanels + 1), stream_));
-        tr.dir = 1;
-        VBK_LAUNCH(k_window_tri, gtri, kTriThreads, sm_tri, stream_, tr);
-    }
+    sweep3(1);
     VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
     if (T > 0) VBK_LAUNCH(k_bwd_flags, gsolve, kSolveThreads, flag_smem, stream_, fs);
     VBK_CHECK_LAUNCH();

@@ -9,8 +9,7 @@
 // chain, one chain per entry of the column, |sigma_i| links long.  sigma_i starts with the column that
 // finished LAST (in the dense tail sigma_i = [i-1, i-3, ..., i-4, i-2]), so a column's chains cannot
 // start before its predecessor is final: per factorisation the critical path is ~Lnz dependent FP64
-// additions (dfl001: 6.96 M of 7.16 M), 8 cycles each on B200.  The second-generation kernel
-// (vbk_factor_tiled.cuh) spent ~150 cycles per link: load, scatter, barrier, add phases of a whole CTA
+// additions (dfl001: 6.96 M of 7.16 M), 8 cycles each on B200.  The round-1 kernel spent ~150 cycles per link: load, scatter, barrier, add phases of a whole CTA
 // in sequence, all of it starting only when the last child had finished.  Here a CTA is a pipeline:
 //
 //   producer warps   form the products of 32 contributors at a time into a ring of shared-memory

@@ -5,7 +5,7 @@
 // subtractions that STARTS with the row that became final last (the first stored row of a column is its
 // elimination-tree parent).  So a column's chain cannot start before its parent is final and is c_i links long:
 // one backward sweep is a critical path of ~Lnz dependent FP64 subtractions (dfl001: 7.0 M), 8 cycles each.  The
-// second-generation kernel (k_bwd_flags, vbk_factor_tiled.cuh) ran loads, products and chain of a 128-entry round in
+// round-1 kernel (k_bwd_flags, vbk_flag_solve.cuh) ran loads, products and chain of a 128-entry round in
 // one warp, one after the other, and started a column's loads only when the parent had finished (~19 cycles per link).
 // Here a CTA is a pipeline over one column:
 //   producer warps  form the products L[k]*z[row_k] of 128 entries at a time into a ring of shared-memory stages;
@@ -15,8 +15,7 @@
 // Columns are claimed in descending order by persistent CTAs; a column only waits for rows with larger indices, which
 // were claimed earlier: no deadlock for any grid.
 #pragma once
-#include "vbk_kernels.cuh"
-#include "vbk_strict_factor.cuh"
+#include "vbk_flag_solve.cuh"
 
 namespace vbk {
 

@@ -1,9 +1,8 @@
-// vbk_fast5.cuh -- dense-window triangular sweeps, second generation (fast mode): 128-row panels with inverted
+// vbk_window_solve.cuh -- dense-window triangular sweeps (fast mode): 128-row panels with inverted
 // diagonal blocks.
 //
-// k_window_tri (vbk_fast2.cuh) hands the sweep from one 32-row panel to the next through a global flag: 134
-// hand-offs for dfl001's window (W = 4277), each one = flag round trip + 32 dependent substitution steps + fence
-// (4.8 us per panel, 640 us per sweep, four sweeps per KKT step: 2.6 of the 11.6 ms of a step, profiles/).  Here
+// A sweep that hands over from one 32-row panel to the next through a global flag pays 134 hand-offs on dfl001's window
+// (4.8 us each, 640 us per sweep, four sweeps per KKT step).  Here
 //   * a panel is 128 rows: 34 hand-offs instead of 134;
 //   * the diagonal blocks are inverted ONCE per factorisation (k_window_tinv), so the triangular solve inside a panel
 //     becomes a 128 x 128 matrix-vector product from shared memory -- no dependent chain at all;
@@ -17,7 +16,7 @@
 // update and the forward test can run after the product; in the backward sweep row r of L^T is zero, so the test
 // runs on the right-hand side BEFORE the product (the zeroed value is what the rows above must see).
 #pragma once
-#include "vbk_fast4.cuh"
+#include "vbk_dense_update.cuh"
 
 namespace vbk {
 
@@ -149,7 +148,11 @@ static __global__ void __launch_bounds__(kTriV3Threads, 1) k_window_tri3(Tri3Arg
             __syncthreads();
             if (tid < kTriPW) {
                 zq[tid] = (q * kTriPW + tid < a.W) ? __ldcg(&a.z[q * kTriPW + tid]) : 0.0;
-                if (lastblk) rothers = __ldcg(&a.racc[(size_t)p * kTriPW + tid]);
+                if (lastblk) {                   // the other slices' partial sums, added in slice order: the same bits every run
+#pragma unroll
+                    for (int s2 = 0; s2 < kTriSplit; ++s2)
+                        if (s2 != own) rothers += __ldcg(&a.racc[((size_t)p * kTriSplit + s2) * kTriPW + tid]);
+                }
             }
             __syncthreads();
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -165,7 +168,7 @@ static __global__ void __launch_bounds__(kTriV3Threads, 1) k_window_tri3(Tri3Arg
         __syncthreads();
         if (!owner) {
             if (pp > 0) {
-                if (tid < kTriPW && sl < pp) atomicAdd(&a.racc[(size_t)p * kTriPW + tid], part[tid] + part[kTriPW + tid]);
+                if (tid < kTriPW && sl < pp) a.racc[((size_t)p * kTriSplit + sl) * kTriPW + tid] = part[tid] + part[kTriPW + tid];
                 __threadfence();
                 __syncthreads();
                 if (tid == 0) atomicAdd(&arrived[p], 1);

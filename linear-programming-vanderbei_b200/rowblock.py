@@ -76,6 +76,7 @@ class RowBlockOps:
         self.full_y = torch.zeros(self.rows_per * self.world, dtype=torch.float64, device=self.device)
         self.scratch = torch.zeros(int(self.lib.vbk_reduce_scratch_doubles()), dtype=torch.float64, device=self.device)
         self.red = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.red_max = torch.zeros(8, dtype=torch.float64, device=self.device)   # max-norms: own buffer (dots and absmax may be in flight together)
         self.launches = 0
 
     # -- partition helpers -------------------------------------------------------------------------
@@ -140,18 +141,18 @@ class RowBlockOps:
         self.launches += 2
         if self.world > 1:
             self.dist.all_reduce(out, op=self.dist.ReduceOp.SUM, group=self.group)
-        return out
+        return out.clone()       # the reduction buffer is reused by the next call: hand out a copy
 
     def absmax(self, vecs):
         """Global max-norms (maxv) of up to 8 partitioned vectors; device tensor [len(vecs)]."""
         k = len(vecs)
         xs, lens = self._ptrs(vecs)
-        out = self.red[:k]
+        out = self.red_max[:k]
         self.lib.vbk_absmax_partial_dev(k, xs, lens, out.data_ptr(), self._stream())
         self.launches += 1
         if self.world > 1:
             self.dist.all_reduce(out, op=self.dist.ReduceOp.MAX, group=self.group)
-        return out
+        return out.clone()       # the reduction buffer is reused by the next call: hand out a copy
 
     # -- algorithmic bytes of one A_x + At_y pair on this rank (SURVEY.md 8d work model) ----------------
     def spmv_bytes(self):

@@ -160,7 +160,7 @@ def north_star_tolerances(lp, method, x, y, status, log, iter_slack=1):
 
 def check_fast_sparse_columns(vbkkt, lib, oracle, lp, method, it):
     """Fast mode keeps the reference's arithmetic for the sparse columns j < T: L, diag and mark of those
-    columns equal the oracle's factor bit for bit (level-scheduled kernels of vbk_fast6.cuh, or the task
+    columns equal the oracle's factor bit for bit (level-scheduled kernels of vbk_sparse_level.cuh, or the task
     kernel -- whichever the handle runs)."""
     E, D, *_ = H.capture_step(oracle, lp, method, it)
     F = H.oracle_factor_for(oracle, lp)

@@ -42,24 +42,17 @@ def test_emu_sliced_columns_bit_exact(vbkkt, emu_lib, oracle_lib, monkeypatch, c
     assert info["ndep"] > 0
 
 
-@pytest.mark.parametrize("which", ["VBK_FACTOR", "VBK_SOLVE"])
-def test_emu_first_generation_kernels_still_bit_exact(vbkkt, emu_lib, oracle_lib, monkeypatch, which):
-    monkeypatch.setenv(which, "simple")
-    P.check_kkt_step(vbkkt, emu_lib, oracle_lib, H.load_fixture("afiro"), "hsd", 26)
-
-
-@pytest.mark.parametrize("name,it,env", [("afiro", 5, {}), ("sc50b", 12, {"VBK_PANEL": "3"}),
-                                         ("sc105", 15, {"VBK_WINDOW_RHO": "0.1", "VBK_PANEL": "5"}),
-                                         ("sc105", 15, {"VBK_WINDOW_RHO": "0.1", "VBK_DENSE": "v2", "VBK_PANEL": "5"}),
+@pytest.mark.parametrize("name,it,env", [("afiro", 5, {}), ("sc50b", 12, {}),
+                                         ("sc105", 15, {"VBK_WINDOW_RHO": "0.1"}),
                                          ("israel", 12, {"VBK_WINDOW_RHO": "0.1"}),
-                                         ("israel", 12, {"VBK_WINDOW_RHO": "0.1", "VBK_WSOLVE": "v2", "VBK_SCHUR": "light"})])
+                                         ("israel", 12, {"VBK_WINDOW_RHO": "0.1", "VBK_SPARSE": "strict"})])
 def test_emu_fast_mode_kkt_step(vbkkt, emu_lib, oracle_lib, monkeypatch, name, it, env):
     """Fast mode: sparse part + Schur assembly + blocked dense LDL^T + dense-window sweeps, several
     panels and a padded (rho < 1) window forced on tiny LPs.  israel at rho = 0.1 has a 131-wide window:
     three of the emulated build's 64-column panels (diagonal block with two sub-blocks, rows below,
-    trailing update) and two of the 128-row panels of the window sweeps (k_window_tri3 with its four column slices and
-    the inverted diagonal blocks of k_window_tinv); VBK_DENSE=v2, VBK_WSOLVE=v2 and VBK_SCHUR=light keep the earlier
-    generations covered."""
+    trailing update) and two of the 128-row panels of the window sweeps (k_window_tri3 with its four column
+    slices and the inverted diagonal blocks of k_window_tinv); VBK_SPARSE=strict runs the sparse columns
+    through the strict slice-task kernel instead of the level kernels."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     P.check_kkt_step_fast(vbkkt, emu_lib, oracle_lib, H.load_fixture(name), "hsd", it)

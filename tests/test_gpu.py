@@ -120,7 +120,7 @@ def test_fast_mode_big_iterates_match_reference_solution(vbkkt, gpu_lib):
 @pytest.mark.parametrize("name,it", [("afiro", 26), ("25fv47", 20), ("pds-02", 20), ("dfl001", 20)])
 def test_fast_mode_sparse_columns_bit_exact(vbkkt, gpu_lib, oracle_lib, name, it):
     """Fast mode keeps the reference's arithmetic for the sparse columns j < T (level-scheduled kernels of
-    vbk_fast6.cuh: contributors in the reference's list order, separately rounded products and sums, exact pivot
+    vbk_sparse_level.cuh: contributors in the reference's list order, separately rounded products and sums, exact pivot
     rule): their part of L, diag and mark equals the strict factor -- itself bit-equal to the reference -- bit for
     bit, dependent pivots included (afiro iterate 26 has two)."""
     lp = H.load_fixture(name)
