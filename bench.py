@@ -278,7 +278,16 @@ def multi_gpu_workload(a, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    a.warmup = max(a.warmup, 3) if a.workload == "rowblock" else max(a.warmup, 1)
+    out = run_batch(a, vb, lib, rank, local_rank, world) if a.workload == "batch" else run_rowblock(a, vb, lib, rank, local_rank, world)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _sync_helpers(world, dev):
+    import torch
+    import torch.distributed as dist
 
     def barrier():
         torch.cuda.synchronize()
@@ -292,45 +301,74 @@ def multi_gpu_workload(a, rank, local_rank, world):
         t = torch.tensor([v], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+    return barrier, max_over_ranks
 
+
+def run_batch(a, vb, lib, rank, local_rank, world):
+    """BASELINE config 4: independent random sparse LPs, LP i on rank i mod world, no collective on the data path.
+    Returns the result dict on rank 0 (None elsewhere).  The process group, if any, is the caller's."""
+    import torch
+    dev = torch.device("cuda", local_rank)
+    barrier, max_over_ranks = _sync_helpers(world, dev)
+    mode = vb.MODE_STRICT if a.batch_mode == "strict" else vb.MODE_FAST
+    warm = max(a.warmup, 1)
     sampler = ClockSampler(local_rank)
-    if a.workload == "batch":
-        B = a.batch_per_gpu
-        nlp = B * world
-        gen = lambda i: vb.workloads.random_sparse_lp(i, a.batch_m, a.batch_n)
-        mine = [gen(i) for i in vb.batch.shard(nlp, rank, world)]
-        vb.batch.solve_local(lib, mine[:1], "hsd", local_rank, mode, 1)              # warm-up (module load, allocator)
-        for _ in range(a.warmup - 1):
-            vb.batch.solve_local(lib, mine[:min(len(mine), a.streams)], "hsd", local_rank, mode, a.streams)
-        sampler.start()
-        barrier()
-        t0 = time.perf_counter()
-        res = None
-        for _ in range(a.steps):
-            res = vb.batch.solve_local(lib, mine, "hsd", local_rank, mode, a.streams)
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        clocks = sampler.summary()
-        ok = all(r["status"] == 0 for r in res)
-        its = float(np.mean([r["iterations"] for r in res]))
-        gap = float(max(abs(r["primal_obj"] - r["dual_obj"]) / max(1.0, abs(r["primal_obj"])) for r in res))
-        if rank == 0:
-            v = nlp * a.steps / dt
-            nbytes_in = sum(12 * lp.nz + 4 * (lp.n + 1) + 8 * (lp.m + lp.n) for lp in mine)
-            out = {"metric": "independent LPs solved per second (hsd)", "value": v, "unit": "LP/s", "n_gpus": world,
-                   "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
-                   "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic random sparse LPs (seed = LP index)",
-                   "config": {"workload": f"batch of {nlp} random sparse LPs m={a.batch_m} n={a.batch_n} (8 nnz/col), "
-                                          f"{B} per GPU, LP i on rank i mod {world}", "mode": a.mode,
-                              "streams_per_gpu": a.streams, "l2": "each LP's factor (Lnz*8 B) exceeds nothing: working sets rotate across LPs",
-                              "parallelism": f"{world} rank(s), no collective on the data path"},
-                   "e2e": {"value": v, "unit": "LP/s", "h2d_bytes_per_step": int(nbytes_in),
-                           "d2h_bytes_per_step": int(sum(8 * (lp.m + lp.n) for lp in mine)),
-                           "note": "vbk_solve_batch takes host arrays and returns host x,y: the timed region is end to end"},
-                   "gpu_launches": None, "clocks": clocks,
-                   "parity": {"all_optimal": bool(ok), "mean_iterations": its, "max_rel_duality_gap": gap}}
-            print(json.dumps(out))
-    else:
+    B = a.batch_per_gpu
+    nlp = B * world
+    gen = lambda i: vb.workloads.random_sparse_lp(i, a.batch_m, a.batch_n)
+    mine = [gen(i) for i in vb.batch.shard(nlp, rank, world)]
+    vb.batch.solve_local(lib, mine[:1], "hsd", local_rank, mode, 1)              # warm-up (module load, allocator)
+    for _ in range(warm - 1):
+        vb.batch.solve_local(lib, mine[:min(len(mine), a.streams)], "hsd", local_rank, mode, a.streams)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    res = None
+    for _ in range(a.batch_steps):
+        res = vb.batch.solve_local(lib, mine, "hsd", local_rank, mode, a.streams)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.summary()
+    ok = all(r["status"] == 0 for r in res)
+    its = float(np.mean([r["iterations"] for r in res]))
+    gap = float(max(abs(r["primal_obj"] - r["dual_obj"]) / max(1.0, abs(r["primal_obj"])) for r in res))
+    # strict-mode sample on rank 0: the same LP in the parity mode, for the iteration count and objective it should have
+    strict_sample = None
+    if rank == 0 and mode != vb.MODE_STRICT and not a.no_strict:
+        r0 = vb.batch.solve_local(lib, mine[:1], "hsd", local_rank, vb.MODE_STRICT, 1)[0]
+        strict_sample = {"lp": 0, "status": r0["status"], "iterations": r0["iterations"], "seconds": r0["seconds"],
+                         "fast_iterations": res[0]["iterations"],
+                         "rel_objective_diff_fast_vs_strict": abs(res[0]["primal_obj"] - r0["primal_obj"]) / max(1.0, abs(r0["primal_obj"]))}
+    if rank != 0:
+        return None
+    v = nlp * a.batch_steps / dt
+    nbytes_in = sum(12 * lp.nz + 4 * (lp.n + 1) + 8 * (lp.m + lp.n) for lp in mine)
+    return {"metric": "independent LPs solved per second (hsd)", "value": v, "unit": "LP/s", "n_gpus": world,
+            "steps": a.batch_steps, "warmup": warm, "ms_per_step": dt / a.batch_steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic random sparse LPs (seed = LP index)",
+            "config": {"workload": f"BASELINE config 4: batch of {nlp} random sparse LPs m={a.batch_m} n={a.batch_n} (8 nnz/col), "
+                                   f"{B} per GPU, LP i on rank i mod {world}", "mode": a.batch_mode,
+                       "streams_per_gpu": a.streams, "host_cores": os.cpu_count(),
+                       "l2": "working sets rotate across LPs (each LP has its own factor object)",
+                       "parallelism": f"{world} rank(s), no collective on the data path"},
+            "e2e": {"value": v, "unit": "LP/s", "h2d_bytes_per_step": int(nbytes_in),
+                    "d2h_bytes_per_step": int(sum(8 * (lp.m + lp.n) for lp in mine)),
+                    "note": "vbk_solve_batch takes host arrays and returns host x,y: the timed region is end to end, symbolic phase included"},
+            "gpu_launches": None, "clocks": clocks,
+            "parity": {"all_optimal": bool(ok), "mean_iterations": its, "max_rel_duality_gap": gap, "strict_sample": strict_sample}}
+
+
+def run_rowblock(a, vb, lib, rank, local_rank, world):
+    """BASELINE config 5: row-block smx / transpose-smx + dot / max-norm all-reduce on the synthetic multicommodity LP.
+    Returns the result dict on rank 0 (None elsewhere)."""
+    import torch
+    import harness as H
+    dev = torch.device("cuda", local_rank)
+    barrier, max_over_ranks = _sync_helpers(world, dev)
+    warm = max(a.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    steps = a.rowblock_steps
+    if True:
         lp = vb.workloads.multicommodity_lp(a.grid, a.commodities)
         kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
         ops = vb.rowblock.RowBlockOps(lib, lp.m, lp.n, lp.kA, lp.iA, lp.A, kAt, iAt, At, dev)
@@ -342,12 +380,8 @@ def multi_gpu_workload(a, rank, local_rank, world):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
         def step():
-            ops.A_x(lx, rho)                       # hsd.c:182
-            ops.At_y(ly, sig)                      # hsd.c:191
-            d = ops.dots([(lx, sig), (ly, rho), (rho, rho), (sig, sig)]).clone()
-            mx = ops.absmax([rho, sig]).clone()
-            return d, mx
-        for _ in range(a.warmup):
+            return ops.step(lx, ly, rho, sig)      # hsd.c:182-195: A x, A^T y, 4 dot products, 2 max-norms
+        for _ in range(warm):
             d, mx = step()
         # parity: the distributed products against a host computation of the same sums
         import scipy.sparse as sp
@@ -358,16 +392,16 @@ def multi_gpu_workload(a, rank, local_rank, world):
         derr = abs(float(d[1]) - dref) / max(1.0, abs(dref))
         assert err < 1e-12 and derr < 1e-10, (err, derr)
         sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
-        for s in range(a.steps):
+        for s in range(steps):
             flush.fill_(s & 0xFF)
             barrier()
             ev[s][0].record()
             step()
             ev[s][1].record()
         barrier()
-        ms = max_over_ranks(float(sum(e0.elapsed_time(e1) for e0, e1 in ev)) / a.steps)
+        ms = max_over_ranks(float(sum(e0.elapsed_time(e1) for e0, e1 in ev)) / steps)
         clocks = sampler.summary()
         # e2e: host vectors in, host results out, per step
         hx, hy = torch.from_numpy(x[ops.c0:ops.c1].copy()).pin_memory(), torch.from_numpy(y[ops.r0:ops.r1].copy()).pin_memory()
@@ -379,33 +413,32 @@ def multi_gpu_workload(a, rank, local_rank, world):
             return d.cpu(), mx.cpu()
         step_host(); barrier()
         t0 = time.perf_counter()
-        for _ in range(a.steps):
+        for _ in range(steps):
             step_host()
         barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / a.steps)
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
         if rank == 0:
             total_bytes = rowblock_bytes(lp.m, lp.n, lp.nz)
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
             hbm = peaks.get("hbm_gbs", 6650.0)
             v = total_bytes / (ms * 1e-3) / 1e9
-            out = {"metric": "row-block smx + dot/maxv GB/s", "value": v, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
-                   "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            out = {"metric": "row-block smx + dot/maxv GB/s", "value": v, "unit": "GB/s", "n_gpus": world, "steps": steps,
+                   "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                    "dtype": "f64", "data": "synthetic multicommodity LP (generator seed 1)",
-                   "config": {"workload": f"multicommodity R={a.grid} K={a.commodities}: m={lp.m} n={lp.n} nz={lp.nz}; step = A x + A^T y "
-                                          "(all-gather + row-block SpMV each) + 4 dot products + 2 max-norms (one all-reduce each)",
+                   "config": {"workload": f"BASELINE config 5: multicommodity R={a.grid} K={a.commodities}: m={lp.m} n={lp.n} nz={lp.nz}; step = A x + A^T y "
+                                          "(all-gather + row-block SpMV each, both all-gathers in flight together) + 4 dot products + 2 max-norms (ONE 48-byte all-gather)",
                               "l2": "flushed between timed steps (256 MiB write)",
-                              "parallelism": f"row blocks over {world} rank(s); NCCL all-gather of x,y and all-reduce of 4+2 doubles"},
+                              "parallelism": f"row blocks over {world} rank(s); NCCL all-gather of x, y and of the 6 partial scalars"},
                    "e2e": {"value": total_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
                            "h2d_bytes_per_step": int(8 * (ops.c1 - ops.c0 + ops.r1 - ops.r0)),
                            "d2h_bytes_per_step": int(8 * (ops.c1 - ops.c0 + ops.r1 - ops.r0) + 48)},
-                   "gpu_launches": 5 * a.steps, "clocks": clocks,
+                   "gpu_launches": 5 * steps, "clocks": clocks,
                    "roofline": {"kernel": "k_spmv_rows + k_dot_partial/k_absmax_partial (whole step)", "bound": "hbm",
                                 "achieved": v / world, "peak": hbm, "unit": "GB/s", "frac": v / world / hbm, "traffic": None,
                                 "note": "per-GPU algorithmic bytes (12 B per nonzero, 8 B per vector entry read or written) over the step time, collectives included"},
                    "parity": {"max_rel_err_Ax": err, "rel_err_dot": derr}}
-            print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+            return out
+    return None
 
 
 def rowblock_bytes(m, n, nz):

@@ -31,6 +31,20 @@ void ldltfac(int m, int n, int *kA, int *iA, double *A, double *dn, double *dm,
 void forwardbackward(double *Dn, double *Dm, double *dx, double *dy);
 /* lp.h:236-239 / ldlt.c:507-513: releases the process-global factor object. */
 void inv_clo(void);
+/* lp.h:213-227 -- the LP-struct forms of the same two calls, for drivers that hold the reference's `LP` (amplio and the
+ * like; ipo itself goes through ldltfac / forwardbackward).  Only the leading members of `LP` are read -- m, n, the CSC
+ * triples (A, iA, kA) and (At, iAt, kAt) -- through the mirror below, which repeats lp.h:34-62 member for member so that
+ * the offsets agree under the platform's C ABI.  Q must be empty (qnz == 0), as it is on every ipo path (ldlt.c:150-153). */
+struct vbk_lp_head {
+    int m, n, nz;
+    double *A; int *iA; int *kA;
+    double *b; double *c; double f; double *r; double *l; double *u;
+    int *varsgn; char **rowlab; char **collab;
+    int qnz; double *Q; int *iQ; int *kQ;
+    double *At; int *iAt; int *kAt;
+};
+void inv_num(void *lp, double *dn, double *dm);                        /* ldlt.c:164-309 */
+int  solve(void *lp, double *Dn, double *Dm, double *c, double *b);    /* ldlt.c:327-425; returns `consistent` */
 
 /* replaces the ipo-relevant part of src/common/linalg.c (declared in src/common/linalg.h:1-8) */
 double dotprod(double *x, double *y, int n);                                   /* linalg.c:17-25  */

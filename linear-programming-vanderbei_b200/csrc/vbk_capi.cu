@@ -87,6 +87,21 @@ void forwardbackward(double* Dn, double* Dm, double* dx, double* dy)
     g_kkt->solve_host(Dn, Dm, dx, dy);
 }
 
+// lp.h:213-227: the LP-struct forms (ldlt.c:164, :327).  The factor object is bound to the first LP seen, like the
+// reference's statics.
+void inv_num(void* lp_, double* dn, double* dm)
+{
+    const vbk_lp_head* lp = static_cast<const vbk_lp_head*>(lp_);
+    if (lp->qnz != 0) { std::fprintf(stderr, "vbkkt: inv_num: quadratic terms (qnz = %d) are not supported\n", lp->qnz); std::exit(1); }
+    ldltfac(lp->m, lp->n, lp->kA, lp->iA, lp->A, dn, dm, lp->kAt, lp->iAt, lp->At, 0);
+}
+int solve(void* lp_, double* Dn, double* Dm, double* c, double* b)
+{
+    (void)lp_;
+    if (!g_kkt) { std::fprintf(stderr, "vbkkt: solve() before inv_num()\n"); std::exit(1); }
+    return g_kkt->solve_host(Dn, Dm, c, b);
+}
+
 void inv_clo(void)
 {
     g_kkt.reset();

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 
 namespace vbk {
@@ -70,7 +71,7 @@ void Symbolic::order(std::vector<std::vector<int>>& adj, std::vector<int>& tier)
         for (auto& a : adj) half += (long long)a.size();
         iL.reserve((size_t)half);  // grows as fill is discovered
     }
-    std::vector<int> stamp(N, 0), others;
+    std::vector<int> stamp(N, 0), estamp(N, 0), others;
     others.reserve(N);
 
     KeyHeap heap(N);
@@ -85,77 +86,131 @@ void Symbolic::order(std::vector<std::vector<int>>& adj, std::vector<int>& tier)
         heap.sift_down(v + 1);
     }
 
-    int tag = 0;
+    // Eliminated nodes are NOT removed from their neighbours' lists on the spot (the reference shifts them out,
+    // ldlt.c:1094-1120): they are recognised by gone[] wherever a list is read and squeezed out the next time the list is
+    // scanned for fill; deg[] carries the live degrees.  clique[u] = the elimination step whose survivors u belonged to
+    // last: that step made its survivors pairwise adjacent, and edges between live nodes never disappear, so a later
+    // step whose survivors all carry one common clique id has no fill to find and no list to scan -- once the graph has
+    // become dense (the heavy top of the elimination tree) a step costs O(degree) instead of O(degree^2).
+    std::vector<int> deg(N), clique(N, -1);
+    std::vector<char> gone(N, 0);
+    for (int v = 0; v < N; ++v) deg[v] = (int)adj[v].size();
+    int tag = 0, etag = 0;
     denwin = N;
+    double tph[6] = {0,0,0,0,0,0};
+    auto now = []{ return std::chrono::steady_clock::now(); };
+    const bool timing = std::getenv("VBK_SYM_STATS") != nullptr;
     for (int i = 0; i < N;) {
+        auto tp0 = now();
         const int pivot = heap.top();
-        const int d = (int)adj[pivot].size();
+        const int d = deg[pivot];
         if (d >= N - 1 - i) denwin = i;  // ldlt.c:1027
         perm[i] = pivot;
         iperm[pivot] = i;
+        {   // the pivot's own list is read several times below: squeeze the eliminated nodes out of it first
+            auto& lst = adj[pivot];
+            size_t w = 0;
+            for (size_t k = 0; k < lst.size(); ++k) if (!gone[lst[k]]) lst[w++] = lst[k];
+            lst.resize(w);
+        }
 
         // neighbours indistinguishable from the pivot join its group (ldlt.c:1037-1054)
         for (int u : adj[pivot]) iperm[u] = i;
         others.clear();
         int iend = i + 1;
         for (int u : adj[pivot]) {
-            bool same = ((int)adj[u].size() == d) && tier[u] == tier[pivot];
+            bool same = (deg[u] == d) && tier[u] == tier[pivot];
             if (same) {
-                for (int w : adj[u]) if (iperm[w] < i) { same = false; break; }
+                for (int w : adj[u]) if (!gone[w] && iperm[w] < i) { same = false; break; }
             }
             if (same) { perm[iend] = u; iperm[u] = iend; ++iend; }
             else others.push_back(u);
         }
 
+        auto tp1 = now();
         // column structures of the group members (ldlt.c:1068-1088); old node ids for now
         for (int ii = i, len = d; ii < iend; ++ii, --len) {
             kL[ii + 1] = kL[ii] + len;
             for (int w : adj[perm[ii]]) {
+                if (gone[w]) continue;
                 int row = iperm[w];
                 if (row > ii || (row == i && w != pivot)) iL.push_back(w);
             }
         }
 
-        // drop the eliminated nodes from the survivors' lists, keeping order (ldlt.c:1094-1120)
-        for (int u : others) {
-            auto& lst = adj[u];
-            lst.erase(std::find(lst.begin(), lst.end(), pivot));
-        }
-        if (iend > i + 1) {
-            for (int u : others) {
-                auto& lst = adj[u];
-                lst.erase(std::remove_if(lst.begin(), lst.end(), [&](int w) { return iperm[w] > i; }),
-                          lst.end());
-            }
-        }
-
+        auto tp2 = now();
         for (int ii = i; ii < iend; ++ii) heap.remove(perm[ii]);  // ldlt.c:1122-1134
+        auto tp3 = now();
+
+        // every group member is adjacent to every survivor (its neighbourhood is the pivot's): they leave the graph
+        const int nelim = iend - i;
+        for (int ii = i; ii < iend; ++ii) gone[perm[ii]] = 1;
+        const int nsurv = (int)others.size();
+        for (int u : others) deg[u] -= nelim;
 
         // pairwise fill among the survivors, appended at the list ends (ldlt.c:1144-1201)
-        for (size_t a = 0; a < others.size(); ++a) {
-            int u = others[a];
-            ++tag;
-            for (int w : adj[u]) stamp[w] = tag;
-            for (size_t b = a + 1; b < others.size(); ++b) {
-                int w = others[b];
-                if (stamp[w] != tag) { adj[u].push_back(w); adj[w].push_back(u); }
+        bool one_clique = nsurv > 0 && clique[others[0]] >= 0;
+        for (int a = 1; a < nsurv && one_clique; ++a) one_clique = clique[others[a]] == clique[others[0]];
+        if (!one_clique) {
+            ++etag;
+            for (int u : others) estamp[u] = etag;
+            for (int a = 0; a < nsurv; ++a) {
+                const int u = others[a];
+                auto& lst = adj[u];
+                ++tag;
+                int have = 0;
+                size_t w = 0;
+                for (size_t k = 0; k < lst.size(); ++k) {
+                    const int v = lst[k];
+                    if (gone[v]) continue;                // eliminated, in this step or an earlier one
+                    lst[w++] = v;
+                    if (stamp[v] != tag) { stamp[v] = tag; have += (estamp[v] == etag); }    // a repeated entry counts once
+                }
+                lst.resize(w);
+                if (have == nsurv - 1) continue;          // u already sees every other survivor
+                for (int b = a + 1; b < nsurv; ++b) {
+                    const int x = others[b];
+                    if (stamp[x] != tag) { lst.push_back(x); adj[x].push_back(u); ++deg[u]; ++deg[x]; }
+                }
             }
+            for (int u : others) clique[u] = i;
         }
 
+        auto tp4 = now();
         // re-key survivors in list order: float, then sink (ldlt.c:1206-1220)
         for (int u : others) {
-            heap.key[u] = (int)adj[u].size() + (tier[u] != 0 ? tier[u] * penalty : 0);
+            heap.key[u] = deg[u] + (tier[u] != 0 ? tier[u] * penalty : 0);
             heap.sift_up(heap.where[u]);
             heap.sift_down(heap.where[u]);
         }
 
         for (int ii = i; ii < iend; ++ii) std::vector<int>().swap(adj[perm[ii]]);
         i = iend;
+        if (timing) { auto tp5 = now(); auto D = [](auto a, auto b){ return std::chrono::duration<double>(b - a).count(); };
+            tph[0] += D(tp0, tp1); tph[1] += D(tp1, tp2); tph[2] += D(tp2, tp3); tph[3] += D(tp3, tp4); tph[4] += D(tp4, tp5); }
     }
 
+    if (timing) std::fprintf(stderr, "vbk ordering phases: group test %.3f, column structures %.3f, heap remove %.3f, fill %.3f, re-key %.3f s\n", tph[0], tph[1], tph[2], tph[3], tph[4]);
+    auto tq0 = now();
     for (int& r : iL) r = iperm[r];  // ldlt.c:1236
-    for (int j = 0; j < N; ++j) std::sort(iL.begin() + kL[j], iL.begin() + kL[j + 1]);  // :1238
+    {
+        // rows ascending inside each column (ldlt.c:1238 sorts every column; the result only depends on the sets): two
+        // bucket passes -- by row, then back by column in ascending row order -- instead of a sort per column
+        const size_t nnz = iL.size();
+        std::vector<int> rcnt((size_t)N + 1, 0), rcol(nnz);
+        for (size_t k = 0; k < nnz; ++k) rcnt[(size_t)iL[k] + 1]++;
+        for (int r = 0; r < N; ++r) rcnt[r + 1] += rcnt[r];
+        {
+            std::vector<int> fill(rcnt.begin(), rcnt.end() - 1);
+            for (int j = 0; j < N; ++j)
+                for (int k = kL[j]; k < kL[j + 1]; ++k) rcol[(size_t)fill[iL[k]]++] = j;
+        }
+        std::vector<int> fill(kL.begin(), kL.end() - 1);
+        for (int r = 0; r < N; ++r)
+            for (int t = rcnt[r]; t < rcnt[r + 1]; ++t) iL[(size_t)fill[rcol[t]]++] = r;
+    }
     iL.shrink_to_fit();
+    if (timing) std::fprintf(stderr, "vbk ordering: map + sort columns %.3f s\n", std::chrono::duration<double>(now() - tq0).count());
 
     narth = 0.0;
     for (int j = 0; j < N; ++j) { double c = kL[j + 1] - kL[j]; narth += c * c; }
@@ -197,8 +252,14 @@ void Symbolic::analyze(int m_, int n_, const int* kA, const int* iA, const int* 
     for (int i = 0; i < m; ++i) tier[n + i] = (pdf == 1) ? 1 : 0;
     dense = 3;  // ldlt.c:814-846 with n1 == 0
 
+    const auto t0 = std::chrono::steady_clock::now();
     order(adj, tier);
+    const auto t1 = std::chrono::steady_clock::now();
     derive(kA, iA, kAt, iAt);
+    if (std::getenv("VBK_SYM_STATS"))
+        std::fprintf(stderr, "vbk symbolic: ordering %.3f s, derived structures %.3f s (N %d, Lnz %d)\n",
+                     std::chrono::duration<double>(t1 - t0).count(),
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(), N, kL[N]);
 }
 
 void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* iAt) {
@@ -341,7 +402,7 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
         col_ntask[j] = (int)task_col.size() - col_task0[j];
     }
 
-    if (std::getenv("VBK_SYM_STATS")) {
+    if (std::getenv("VBK_SYM_STATS") && std::atoi(std::getenv("VBK_SYM_STATS")) >= 2) {
         // how much of the factorisation's work lies in contributor segments that cover every row of their task
         long long full_pairs = 0, part_pairs = 0, empty_pairs = 0, full_prod = 0, part_prod = 0, run_prod = 0;
         for (int t = 0; t < (int)task_col.size(); ++t) {

@@ -77,6 +77,8 @@ class RowBlockOps:
         self.scratch = torch.zeros(int(self.lib.vbk_reduce_scratch_doubles()), dtype=torch.float64, device=self.device)
         self.red = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.red_max = torch.zeros(8, dtype=torch.float64, device=self.device)   # max-norms: own buffer (dots and absmax may be in flight together)
+        self.red6 = torch.zeros(6, dtype=torch.float64, device=self.device)            # this rank's 4 sums + 2 maxima (step)
+        self.red6_all = torch.zeros(6 * self.world, dtype=torch.float64, device=self.device)
         self.launches = 0
 
     # -- partition helpers -------------------------------------------------------------------------
@@ -153,6 +155,40 @@ class RowBlockOps:
         if self.world > 1:
             self.dist.all_reduce(out, op=self.dist.ReduceOp.MAX, group=self.group)
         return out.clone()       # the reduction buffer is reused by the next call: hand out a copy
+
+    # -- one interior-point residual step, collectives overlapped -------------------------------------
+    def step(self, x_local, y_local, rho, sig):
+        """rho = (A x)[rows], sig = (A^T y)[cols] and the six scalars hsd.c:182-195 needs from them --
+        x.sig, y.rho, rho.rho, sig.sig (sums) and max|rho|, max|sig| -- with as little exposed communication as the
+        partition allows: both all-gathers are issued at once (NCCL's own stream) and each SpMV waits only for its own
+        operand, and the six partial scalars of all ranks travel in ONE small all-gather; every rank then adds (resp.
+        maximises) them in rank order, so all ranks hold bit-identical results.  Returns (sums[4], maxes[2])."""
+        if self.world > 1:
+            hx = self.dist.all_gather_into_tensor(self.full_x, x_local, group=self.group, async_op=True)
+            hy = self.dist.all_gather_into_tensor(self.full_y, y_local, group=self.group, async_op=True)
+            hx.wait()
+        else:
+            self.full_x.copy_(x_local); self.full_y.copy_(y_local)
+        ptr, idx, val, _ = self.rowblk
+        self.lib.vbk_spmv_rows_dev(self.r1 - self.r0, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(),
+                                   self.full_x.data_ptr(), rho.data_ptr(), self._stream())
+        if self.world > 1:
+            hy.wait()
+        ptr, idx, val, _ = self.colblk
+        self.lib.vbk_spmv_rows_dev(self.c1 - self.c0, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(),
+                                   self.full_y.data_ptr(), sig.data_ptr(), self._stream())
+        pairs = [(x_local, sig), (y_local, rho), (rho, rho), (sig, sig)]
+        xs, lens = self._ptrs([p[0] for p in pairs])
+        ys, _ = self._ptrs([p[1] for p in pairs])
+        self.lib.vbk_dots_partial_dev(4, xs, ys, lens, self.red6.data_ptr(), self.scratch.data_ptr(), self._stream())
+        vs, vlens = self._ptrs([rho, sig])
+        self.lib.vbk_absmax_partial_dev(2, vs, vlens, self.red6[4:].data_ptr(), self._stream())
+        self.launches += 5
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.red6_all, self.red6, group=self.group)
+            allv = self.red6_all.view(self.world, 6)
+            return allv[:, :4].sum(dim=0), allv[:, 4:].amax(dim=0)
+        return self.red6[:4].clone(), self.red6[4:].clone()
 
     # -- algorithmic bytes of one A_x + At_y pair on this rank (SURVEY.md 8d work model) ----------------
     def spmv_bytes(self):

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", header))
     names -= {"defined", "C"}
     decl = {n for n in names if re.search(r"\b(void|int|double|long|char|vbk_kkt)\b[\s\*]+" + n + r"\s*\(", header)}
-    assert {"ldltfac", "forwardbackward", "smx", "atnum", "dotprod", "maxv", "inv_clo",
+    assert {"ldltfac", "forwardbackward", "smx", "atnum", "dotprod", "maxv", "inv_clo", "inv_num", "solve",
             "vbk_solver_hsd", "vbk_solver_intpt", "vbk_kkt_create", "vbk_solve_lp"} <= decl
     for n in sorted(decl):
         assert hasattr(product_lib, n), f"libvbkkt.so does not export {n}"

@@ -46,7 +46,14 @@ def _rowblock_worker(rank, world, port, out):
         sig = ops.At_y(ops.local_y(y)).numpy()[: ops.c1 - ops.c0].copy()
         d = ops.dots([(ops.local_x(x), ops.local_x(x)), (ops.local_y(y), ops.local_y(w))]).numpy().copy()
         mx = ops.absmax([ops.local_x(x), ops.local_y(y)]).numpy().copy()
-        np.savez(out + f".{rank}.npz", rho=rho, sig=sig, d=d, mx=mx, r=np.array([ops.r0, ops.r1, ops.c0, ops.c1]))
+        # the fused step (both all-gathers in flight, one small all-gather for the six scalars)
+        import torch
+        rho2 = torch.zeros(ops.rows_per, dtype=torch.float64)
+        sig2 = torch.zeros(ops.cols_per, dtype=torch.float64)
+        sums, maxes = ops.step(ops.local_x(x), ops.local_y(y), rho2, sig2)
+        np.savez(out + f".{rank}.npz", rho=rho, sig=sig, d=d, mx=mx, r=np.array([ops.r0, ops.r1, ops.c0, ops.c1]),
+                 rho2=rho2.numpy()[: ops.r1 - ops.r0].copy(), sig2=sig2.numpy()[: ops.c1 - ops.c0].copy(),
+                 sums=sums.numpy().copy(), maxes=maxes.numpy().copy())
     finally:
         dist.destroy_process_group()
 
@@ -74,6 +81,13 @@ def test_rowblock_smx_dot_maxv_gloo(tmp_path, emu_lib, oracle_lib, world):
         assert abs(z["d"][0] - x @ x) <= 1e-13 * (x @ x)
         assert abs(z["d"][1] - y @ w) <= 1e-13 * max(1.0, np.abs(y * w).sum())
         assert z["mx"][0] == np.abs(x).max() and z["mx"][1] == np.abs(y).max()
+        # fused step: same products bit for bit, the six scalars identical on every rank
+        assert np.array_equal(z["rho2"], z["rho"]) and np.array_equal(z["sig2"], z["sig"])
+        z0 = np.load(out + ".0.npz")
+        assert np.array_equal(z["sums"], z0["sums"]) and np.array_equal(z["maxes"], z0["maxes"])
+        ref = np.array([x @ sig_ref, y @ rho_ref, rho_ref @ rho_ref, sig_ref @ sig_ref])
+        assert np.allclose(z["sums"], ref, rtol=1e-12, atol=1e-12)
+        assert z["maxes"][0] == np.abs(rho_ref).max() and z["maxes"][1] == np.abs(sig_ref).max()
     assert np.array_equal(rho, rho_ref) and np.array_equal(sig, sig_ref)
 
 
