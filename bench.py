@@ -460,10 +460,17 @@ def main():
     # dfl001 is the largest netlib LP BASELINE.json's config 2 names (FP64-bound factor, ~90 flop/B)
     ap.add_argument("--workload", default=os.environ.get("VBK_BENCH_WORKLOAD", "dfl001"))
     ap.add_argument("--iterate", type=int, default=20)
-    # fast = the performance mode (dense-window factorisation, re-associated sums; parity by tolerance);
-    # strict = bit-exact replay of the reference's rounding order (reported beside it at N=1)
-    ap.add_argument("--mode", default="fast", choices=["strict", "fast"])
-    ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode side measurement")
+    # strict (default, the headline) = bit-exact replay of the reference's rounding order: the only mode that meets the
+    # north_star tolerances on the whole netlib suite; fast = dense-window factorisation with re-associated sums, parity
+    # by tolerance on the robust problems only (reported beside it at N=1 as `fast_mode`, with that caveat)
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--no-strict", action="store_true", help="skip the other mode's side measurement")
+    ap.add_argument("--no-solve-time", action="store_true", help="skip the full-solve timings (solve_time) at N=1")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the batch / row-block workloads attached to the line")
+    ap.add_argument("--batch-mode", default="fast", choices=["strict", "fast"],
+                    help="batch workload: arithmetic mode (fast: tolerance parity, all LPs checked optimal + one strict sample)")
+    ap.add_argument("--batch-steps", type=int, default=1)
+    ap.add_argument("--rowblock-steps", type=int, default=20)
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="batch workload: LPs per GPU per step (default: 2 per solver stream, at least 8)")
     ap.add_argument("--batch-m", type=int, default=2000)
     ap.add_argument("--batch-n", type=int, default=4000)
@@ -481,11 +488,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if a.streams <= 0:
+        a.streams = max(2, min(16, (os.cpu_count() or 8) // max(world, 1)))
+    if a.batch_per_gpu <= 0:
+        a.batch_per_gpu = max(8, 4 * a.streams)
     if a.workload in ("batch", "rowblock"):
-        if a.streams <= 0:
-            a.streams = max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))
-        if a.batch_per_gpu <= 0:
-            a.batch_per_gpu = max(8, 2 * a.streams)
+        if a.workload == "batch":
+            a.batch_steps = max(a.batch_steps, 1)
+        else:
+            a.rowblock_steps = a.steps
         return multi_gpu_workload(a, rank, local_rank, world)
 
     lp, it = load_workload(a.workload, a.iterate)
@@ -632,11 +643,24 @@ def main():
     wy, wx, wgy, wgx = (torch.empty_like(t).pin_memory() for t in (hry, hrx, hb, hc))
     dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
 
+    # The reference's own call sequence (hsd.c:218-228) on the B1 plugin symbols themselves: ldltfac with the m/n and
+    # A/At arguments swapped exactly as hsd.c passes them, then two forwardbackward calls.  The process-global factor
+    # object behind these symbols (ldlt.c:108-120) is separate from the handle K above: it analyses once, here.
+    kAt_h, iAt_h, At_h = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    kA_h, iA_h, A_h = (np.ascontiguousarray(lp.kA, dtype=np.int32), np.ascontiguousarray(lp.iA, dtype=np.int32),
+                       np.ascontiguousarray(lp.A, dtype=np.float64))
+    kAt_h, iAt_h, At_h = (np.ascontiguousarray(kAt_h, dtype=np.int32), np.ascontiguousarray(iAt_h, dtype=np.int32),
+                          np.ascontiguousarray(At_h, dtype=np.float64))
+    lib.inv_clo()
+    lib.vbk_set_device(local_rank)
+    lib.vbk_set_mode(mode)
+
     def step_host():
         wy.copy_(hry); wx.copy_(hrx); wgy.copy_(hb); wgx.copy_(hc)
-        lib.vbk_kkt_factor(K.h, dp(hE), dp(hD))
-        lib.vbk_kkt_solve(K.h, dp(hE), dp(hD), dp(wy), dp(wx))
-        lib.vbk_kkt_solve(K.h, dp(hE), dp(hD), dp(wgy), dp(wgx))
+        lib.ldltfac(lp.n, lp.m, H.ptr_i(kAt_h), H.ptr_i(iAt_h), H.ptr_d(At_h), dp(hE), dp(hD),
+                    H.ptr_i(kA_h), H.ptr_i(iA_h), H.ptr_d(A_h), 1)                       # hsd.c:218
+        lib.forwardbackward(dp(hE), dp(hD), dp(wy), dp(wx))                              # hsd.c:223
+        lib.forwardbackward(dp(hE), dp(hD), dp(wgy), dp(wgx))                            # hsd.c:228
 
     for _ in range(2):
         step_host()
@@ -651,93 +675,172 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     clocks = sampler.summary()
+    lib.inv_clo()
     assert np.array_equal(wy.numpy(), sol_y), "host-buffer path and device-pointer path disagree"
     e2e = {"value": world * flops_step / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(8 * N + 2 * 16 * N), "d2h_bytes_per_step": int(2 * 8 * N)}
+           "h2d_bytes_per_step": int(8 * N + 2 * 16 * N), "d2h_bytes_per_step": int(2 * 8 * N),
+           "api": "ldltfac + 2 x forwardbackward (the reference's plugin symbols, src/ipo/ldlt.h:1-20), pinned host arrays"}
 
-    if rank != 0:
-        if dist:
-            dist.destroy_process_group()
-        return
+    def rank0_line():
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            cpu = cpu_measure(lp, it, flops_step, a.cpu_budget, 200)
+        # roofline of the dominant kernel (numeric LDL^T): algorithmic bytes / flops per launch
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        fac_s = float(np.mean(fac_ms)) * 1e-3
+        b_fac = 12.0 * K.lnz + 8.0 * K.lnz + 2 * 12.0 * nz + 24.0 * N
+        fp64_peak = float(lib.vbk_measure_fp64_tflops(local_rank))
+        fp64 = {"achieved_tflops": K.narth / fac_s / 1e12, "peak_tflops": fp64_peak,
+                "frac": K.narth / fac_s / 1e12 / max(fp64_peak, 1e-9),
+                "peak_source": "measured here (DFMA yardstick kernel, vbk_measure_fp64_tflops; DMMA measures the same "
+                               "37 TFLOP/s, scratch/ubench.cu); MEASURED_PEAKS.json has no FP64 entry"}
+        hbm = {"achieved_gbs": b_fac / fac_s / 1e9, "peak_gbs": hbm_peak, "frac": b_fac / fac_s / 1e9 / hbm_peak,
+               "peak_source": peak_src}
+        # a factorisation is held to the FP64 roofline iff its arithmetic intensity (reference flop count over
+        # algorithmic bytes) exceeds peak_FP64 / peak_HBM (~6 flop/B), otherwise to HBM
+        intensity = K.narth / b_fac
+        fp64_bound = intensity > fp64_peak * 1e12 / (hbm_peak * 1e9)
+        kname = ("numeric factorisation = k_factor_pipe (strict LDL^T: pipelined slice tasks, csrc/vbk_strict_factor.cuh)"
+                 if a.mode == "strict" else
+                 "numeric factorisation = k_sparse_level / k_factor_pipe (sparse columns) + k_schur_window2 + per 128-column panel "
+                 "k_panel_diag, k_panel_rows_m, k_dense_update_m<64,64> (strip), k_dense_update_m<128,64> (DMMA rank-128 update)")
+        # dependent-chain model of the strict factorisation: one rounded FP64 addition per contributor link of the
+        # critical path (~Lnz links), 8.1 cycles each (profiles/r01_ubench.txt) at the sampled SM clock
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        floor_ns = 8.1 / (sm_mhz * 1e-3)
+        chain = {"links": int(K.lnz), "ns_per_link": fac_s * 1e9 / max(K.lnz, 1), "floor_ns_per_link": floor_ns,
+                 "frac_of_floor": floor_ns / (fac_s * 1e9 / max(K.lnz, 1)),
+                 "note": "strict mode is a chain of ~Lnz dependent rounded additions by construction (SURVEY 8d): this is the bound it is held to"}
+        roofline = {"kernel": kname, "bound": "tensor" if fp64_bound else "hbm",
+                    "achieved": fp64["achieved_tflops"] if fp64_bound else hbm["achieved_gbs"],
+                    "peak": fp64_peak if fp64_bound else hbm_peak, "unit": "TFLOP/s" if fp64_bound else "GB/s",
+                    "frac": fp64["frac"] if fp64_bound else hbm["frac"],
+                    "traffic": None, "traffic_note": "not measured by this run; ncu DRAM bytes per factorisation are in profiles/ (r02_summary.md)",
+                    "algorithmic_bytes": b_fac,
+                    "peak_source": fp64["peak_source"] if fp64_bound else peak_src,
+                    "flop_per_byte": intensity, "kernel_ms": fac_s * 1e3, "share_of_step": fac_s * 1e3 / ms_per_step,
+                    "fp64": fp64, "hbm": hbm, "dependent_chain": chain if a.mode == "strict" else None,
+                    "note": ("strict mode replays the reference's rounding order: latency-bound by design (SURVEY 8d), see dependent_chain"
+                             if a.mode == "strict" else
+                             "flops = the reference's own count narth (ldlt.c:1243-1248); the dense window executes more "
+                             "(padding to rho = 0.06), so the pipe is busier than this fraction says")}
 
-    # roofline of the dominant kernel (numeric LDL^T): algorithmic bytes / flops per launch
-    peaks = {}
-    pk = ROOT / "MEASURED_PEAKS.json"
-    if pk.exists():
-        peaks = json.loads(pk.read_text())
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    fac_s = float(np.mean(fac_ms)) * 1e-3
-    b_fac = 12.0 * K.lnz + 8.0 * K.lnz + 2 * 12.0 * nz + 24.0 * N
-    fp64_peak = float(lib.vbk_measure_fp64_tflops(local_rank))
-    fp64 = {"achieved_tflops": K.narth / fac_s / 1e12, "peak_tflops": fp64_peak,
-            "frac": K.narth / fac_s / 1e12 / max(fp64_peak, 1e-9),
-            "peak_source": "measured here (DFMA yardstick kernel, vbk_measure_fp64_tflops; DMMA measures the same "
-                           "37 TFLOP/s, scratch/ubench.cu); MEASURED_PEAKS.json has no FP64 entry"}
-    hbm = {"achieved_gbs": b_fac / fac_s / 1e9, "peak_gbs": hbm_peak, "frac": b_fac / fac_s / 1e9 / hbm_peak,
-           "peak_source": peak_src}
-    # a factorisation is held to the FP64 roofline iff its arithmetic intensity (reference flop count over
-    # algorithmic bytes) exceeds peak_FP64 / peak_HBM (~6 flop/B), otherwise to HBM
-    intensity = K.narth / b_fac
-    fp64_bound = intensity > fp64_peak * 1e12 / (hbm_peak * 1e9)
-    kname = ("k_factor_tiled (strict)" if a.mode == "strict" else
-             "numeric factorisation = k_factor_tiled (sparse columns) + k_schur_window + per 128-column panel "
-             "k_panel_diag, k_panel_rows, k_dense_update_strip, k_dense_update_m (DMMA rank-128 update)")
-    # DRAM traffic of one factorisation, measured once under ncu (profiles/r01_traffic.json); null when this workload
-    # or mode has no capture
-    traffic = None
-    tj = ROOT / "profiles" / "r01_traffic.json"
-    if a.mode == "fast" and tj.exists():
-        ent = json.loads(tj.read_text()).get(a.workload.split(":")[0] if a.workload.startswith("mcf") and a.workload in ("mcf", "mcf:32:25") else a.workload)
-        if isinstance(ent, dict):
-            traffic = ent.get("bytes_per_factorisation")
-    roofline = {"kernel": kname, "bound": "tensor" if fp64_bound else "hbm",
-                "achieved": fp64["achieved_tflops"] if fp64_bound else hbm["achieved_gbs"],
-                "peak": fp64_peak if fp64_bound else hbm_peak, "unit": "TFLOP/s" if fp64_bound else "GB/s",
-                "frac": fp64["frac"] if fp64_bound else hbm["frac"], "traffic": traffic, "algorithmic_bytes": b_fac,
-                "peak_source": fp64["peak_source"] if fp64_bound else peak_src,
-                "flop_per_byte": intensity, "kernel_ms": fac_s * 1e3, "share_of_step": fac_s * 1e3 / ms_per_step,
-                "fp64": fp64, "hbm": hbm,
-                "note": ("strict mode replays the reference's rounding order and is latency-bound by design (SURVEY 8d)"
-                         if a.mode == "strict" else
-                         "flops = the reference's own count narth (ldlt.c:1243-1248); the dense window executes more "
-                         "(padding to rho = 0.25), so the pipe is busier than this fraction says")}
-    strict = None
-    if a.mode == "fast" and not a.no_strict and world == 1:
-        # the same step in strict mode (bit-exact replay of the reference's operation order)
-        K2 = H.kkt_for(vb, lib, lp, device=local_rank, mode=vb.MODE_STRICT)
-        s2 = torch.cuda.ExternalStream(K2.stream, device=dev)
-        def step_strict():
-            with torch.cuda.stream(s2):
-                fy.copy_(ry_d); fx.copy_(rx_d); gy.copy_(b_d); gx.copy_(c_d)
-            K2.factor_dev(E_d.data_ptr(), D_d.data_ptr())
-            K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr())
-            K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), gy.data_ptr(), gx.data_ptr())
+        def side_mode(other):
+            """the same step in the other arithmetic mode"""
+            K2 = H.kkt_for(vb, lib, lp, device=local_rank, mode=other)
+            s2 = torch.cuda.ExternalStream(K2.stream, device=dev)
+            def step2():
+                with torch.cuda.stream(s2):
+                    fy.copy_(ry_d); fx.copy_(rx_d); gy.copy_(b_d); gx.copy_(c_d)
+                K2.factor_dev(E_d.data_ptr(), D_d.data_ptr())
+                K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr())
+                K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), gy.data_ptr(), gx.data_ptr())
+            torch.cuda.synchronize()
+            for _ in range(3):
+                step2()
+            K2.sync()
+            ry2, rx2 = fy.cpu().numpy(), fx.cpu().numpy()
+            bit = bool(np.array_equal(ry2, it["sol_y"]) and np.array_equal(rx2, it["sol_x"]))
+            err2 = float(max(np.max(np.abs(ry2 - it["sol_y"])) / max(np.max(np.abs(it["sol_y"])), 1e-300),
+                             np.max(np.abs(rx2 - it["sol_x"])) / max(np.max(np.abs(it["sol_x"])), 1e-300)))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nrep = 5
+            e0.record(s2)
+            for _ in range(nrep):
+                step2()
+            e1.record(s2); K2.sync(); torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / nrep
+            fk = float(lib.vbk_kkt_last_factor_kernel_ms(K2.h))
+            K2.close()
+            return {"ms_per_step": ms2, "value": flops_step / (ms2 * 1e-3) / 1e9, "unit": "GFLOP/s",
+                    "bit_equal_to_reference": bit, "max_rel_err_kkt_step": err2, "factor_kernel_ms": fk,
+                    "fp64_frac": K.narth / (fk * 1e-3) / 1e12 / max(fp64_peak, 1e-9)}
+
+        strict = fast = None
+        if not a.no_strict and world == 1 and not synthetic:
+            if a.mode == "fast":
+                strict = side_mode(vb.MODE_STRICT)
+                strict["note"] = "same step, strict arithmetic mode: reproduces the reference's golden logs byte for byte"
+            else:
+                fast = side_mode(vb.MODE_FAST)
+                fast["note"] = ("same step, fast mode: dense-window factorisation with re-associated sums.  NOT a parity mode: full "
+                                "solves stay inside the north_star tolerances on the robust problems only (profiles/r01_fast_sweep.md: "
+                                "55 of 86 netlib LPs; see solve_time.in_tolerance for the three BASELINE names)")
+
+        # full solves, device-resident METHOD=hsd (BASELINE's metric starts with "LP solve time"): strict, fast, and the
+        # reference on one host core where that is affordable inside the bench
+        solve_time = None
+        if world == 1 and not a.no_solve_time and not synthetic:
+            solve_time = {}
+            for name in ("25fv47", "pilot87", a.workload if a.workload not in ("25fv47", "pilot87") else "dfl001"):
+                try:
+                    lpx = H.load_fixture(name)
+                except Exception:
+                    continue
+                ent = {}
+                t0 = time.perf_counter()
+                st, log, x, y, _ = H.solve_via(vb, lib, lpx, "hsd", mode=vb.MODE_STRICT)
+                ent["strict_s"] = time.perf_counter() - t0
+                ent["strict_log_identical_to_golden"] = bool(log == str(lpx.extra["hsd_log"]))
+                ent["strict_x_bit_equal"] = bool(np.array_equal(x, lpx.extra["hsd_x"]))
+                ent["iterations"] = len(H.iteration_lines(log))
+                t0 = time.perf_counter()
+                stf, logf, xf, yf, _ = H.solve_via(vb, lib, lpx, "hsd", mode=vb.MODE_FAST)
+                ent["fast_s"] = time.perf_counter() - t0
+                obj_r = float(lpx.c @ lpx.extra["hsd_x"])
+                rel = abs(float(lpx.c @ xf) - obj_r) / max(1.0, abs(obj_r))
+                dit = abs(len(H.iteration_lines(logf)) - ent["iterations"])
+                ent["fast"] = {"status": int(stf), "reference_status": int(lpx.extra["hsd_status"]), "iteration_diff": int(dit), "objective_rel_err": rel,
+                               "in_tolerance": bool(stf == int(lpx.extra["hsd_status"]) and dit <= 1 and rel <= 1e-8)}
+                if name == "25fv47":
+                    # fresh process: the reference keeps ONE factor object per process (ldlt.c:108-120) and would reuse
+                    # the symbolic phase of whatever LP it saw first
+                    code = ("import sys, time; sys.path.insert(0, %r); import harness as H; ref = H.load_ref('hsd'); "
+                            "lp = H.load_fixture(%r); t0 = time.perf_counter(); H.call_solver(ref.solver, lp); "
+                            "print('CPU_S', time.perf_counter() - t0)" % (str(ROOT / "tests"), name))
+                    try:
+                        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+                        for ln in r.stdout.splitlines():
+                            if ln.startswith("CPU_S"):
+                                ent["cpu_s"] = float(ln.split()[1])
+                                ent["cpu"] = "compiled reference, 1 host core, measured here (own process)"
+                    except Exception:
+                        pass
+                if "cpu_s" not in ent and cpu is not None and name == a.workload:
+                    ent["cpu_s_estimate"] = cpu["ms_per_step"] * 1e-3 * ent["iterations"]
+                    ent["cpu"] = "estimate: measured reference ms per KKT step (cpu_baseline) x iterations; the full CPU solve takes minutes"
+                solve_time[name] = ent
+
+        out = {"metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "netlib LP fixture + oracle-generated hsd iterate (tests/golden)",
+               "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+               "cpu_baseline": cpu, "strict_mode": strict, "fast_mode": fast, "solve_time": solve_time,
+               "flops_per_step": flops_step, "rawsolves_per_step": raw_per_step,
+               "parity": ({"kkt_residual_rel": err, "note": "synthetic LP: residual of the solved KKT system, no stored reference solution"}
+                          if a.workload.startswith("mcf") else {"bit_equal_to_reference": bit_equal, "max_rel_err": err}),
+               "symbolic": {"N": N, "lnz": K.lnz, "narth": K.narth, "levels": K.nlevels, "supernodes": K.nsupernodes}}
+        return out
+
+    out = rank0_line() if rank == 0 else None
+    K.close()
+    if world > 1 and not a.no_sharded:
+        # the two workloads that shard (SURVEY 8e), measured on the same ranks in the same run and attached to the line
         torch.cuda.synchronize()
-        step_strict(); K2.sync()
-        bit = bool(np.array_equal(fy.cpu().numpy(), it["sol_y"]) and np.array_equal(fx.cpu().numpy(), it["sol_x"]))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nstrict = 2
-        e0.record(s2)
-        for _ in range(nstrict):
-            step_strict()
-        e1.record(s2); K2.sync(); torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / nstrict
-        strict = {"ms_per_step": ms2, "value": flops_step / (ms2 * 1e-3) / 1e9, "unit": "GFLOP/s",
-                  "bit_equal_to_reference": bit, "factor_kernel_ms": float(lib.vbk_kkt_last_factor_kernel_ms(K2.h)),
-                  "note": "same step, strict arithmetic mode: reproduces the reference's golden logs byte for byte"}
-        K2.close()
-    cpu = None
-    if not a.no_cpu_baseline and world == 1:
-        cpu = cpu_measure(lp, it, flops_step, a.cpu_budget, 200)
-    out = {"metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "netlib LP fixture + oracle-generated hsd iterate (tests/golden)",
-           "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-           "cpu_baseline": cpu, "strict_mode": strict, "flops_per_step": flops_step, "rawsolves_per_step": raw_per_step,
-           "parity": ({"kkt_residual_rel": err, "note": "synthetic LP: residual of the solved KKT system, no stored reference solution"}
-                      if a.workload.startswith("mcf") else {"bit_equal_to_reference": bit_equal, "max_rel_err": err}),
-           "symbolic": {"N": N, "lnz": K.lnz, "narth": K.narth, "levels": K.nlevels, "supernodes": K.nsupernodes}}
-    print(json.dumps(out))
+        dist.barrier()
+        sb = run_batch(a, vb, lib, rank, local_rank, world)
+        dist.barrier()
+        a.rowblock_steps = max(a.rowblock_steps, 10)
+        sr = run_rowblock(a, vb, lib, rank, local_rank, world)
+        if rank == 0:
+            out["sharded"] = {"batch": sb, "rowblock": sr,
+                              "note": "BASELINE configs 4 and 5 on the same N ranks; the primary metric above is N independent replicas of the KKT step"}
+    if rank == 0:
+        print(json.dumps(out))
     if dist:
         dist.destroy_process_group()
 
