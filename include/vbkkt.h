@@ -8,8 +8,8 @@
  *   B1  the reference's plugin symbols, exact signatures, so that the reference's C driver links
  *       libvbkkt.so in place of ldlt.o and the linalg.o member of common.a (src/ipo/makefile:49-64);
  *   B2  the METHOD plugin `solver` (same signature/stdout/status as src/ipo/hsd.c:27, intpt.c:33),
- *       device-resident; exported as vbk_solver_hsd / vbk_solver_intpt here and as plain `solver`
- *       by the two one-function shims libvbkkt_hsd.so / libvbkkt_intpt.so;
+ *       device-resident; exported as vbk_solver_hsd / vbk_solver_hsdls / vbk_solver_intpt here and as plain
+ *       `solver` by the one-function shims libvbkkt_hsd.so / libvbkkt_hsdls.so / libvbkkt_intpt.so;
  *   H   a handle-based API (no reference equivalent: the reference has one process-global factor
  *       object, src/ipo/ldlt.c:108-120) for tests, the batch driver and the bench.
  */
@@ -59,6 +59,10 @@ double maxv(double *x, int n);                                                 /
 int vbk_solver_hsd(int m, int n, int nz, int *iA, int *kA, double *A, double *b, double *c, double f,
                    double *x, double *y, double *w, double *z);
 int vbk_solver_intpt(int m, int n, int nz, int *iA, int *kA, double *A, double *b, double *c, double f,
+                     double *x, double *y, double *w, double *z);
+/* METHOD = hsdls (src/ipo/hsdls.c:37): the long-step variant of hsd, per-component line search (hsdls.c:296-336),
+ * up to 600 iterations, status 7 = numerical problem.  Plain `solver` in libvbkkt_hsdls.so. */
+int vbk_solver_hsdls(int m, int n, int nz, int *iA, int *kA, double *A, double *b, double *c, double f,
                      double *x, double *y, double *w, double *z);
 
 /* ------------------------------------------------------------------------------------------------
@@ -122,7 +126,7 @@ typedef struct vbk_profile {
     long long lnz;
     double narth;
 } vbk_profile;
-/* method: 0 = hsd, 1 = intpt.  Like vbk_solver_* but on an explicit device/mode, const inputs, no
+/* method: 0 = hsd, 1 = intpt, 2 = hsdls.  Like vbk_solver_* but on an explicit device/mode, const inputs, no
  * ownership quirks (w,z are not touched), optional profile. */
 int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const int *iA, const int *kA,
                  const double *A, const double *b, const double *c, double f,
@@ -144,7 +148,7 @@ typedef struct vbk_lp_desc {
     double primal_obj, dual_obj;      /* out: c.x + f, b.y + f (solve.c:254-255)          */
     double seconds;                   /* out: wall time of this LP's solve                */
 } vbk_lp_desc;
-/* method: 0 = hsd, 1 = intpt.  Returns the number of LPs whose status is not 0. */
+/* method: 0 = hsd, 1 = intpt, 2 = hsdls.  Returns the number of LPs whose status is not 0. */
 int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp_desc *lps, int nstreams);
 
 /* ------------------------------------------------------------------------------------------------

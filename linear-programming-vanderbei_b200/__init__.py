@@ -317,13 +317,13 @@ def capture_iterate(method, m, n, nz, iA, kA, A, b, c, f, it, device=0, mode=MOD
 
 def solve_lp(method, m, n, nz, iA, kA, A, b, c, f=0.0, device=0, mode=MODE_STRICT, profile=False, lib=None):
     """METHOD plugin on explicit device/mode: ``method`` is "hsd" (reference src/ipo/hsd.c:27) or
-    "intpt" (src/ipo/intpt.c:33).  Prints the reference's iteration log to stdout.
+    "intpt" (src/ipo/intpt.c:33) or "hsdls" (src/ipo/hsdls.c:37).  Prints the reference's iteration log to stdout.
     Returns (status, x[n], y[m], profile-dict-or-None)."""
     lib = lib or load()
     iA, kA, A, b, c = _ai(iA), _ai(kA), _ad(A), _ad(b), _ad(c)
     x = np.zeros(n + m, dtype=np.float64)
     y = np.zeros(n + m, dtype=np.float64)
     prof = Profile() if profile else None
-    st = lib.vbk_solve_lp(0 if method == "hsd" else 1, device, mode, m, n, nz, _i(iA), _i(kA), _d(A),
+    st = lib.vbk_solve_lp({"hsd": 0, "intpt": 1, "hsdls": 2}[method], device, mode, m, n, nz, _i(iA), _i(kA), _d(A),
                           _d(b), _d(c), float(f), _d(x), _d(y), C.byref(prof) if profile else None)
     return int(st), x[:n].copy(), y[:m].copy(), (prof.as_dict() if profile else None)

@@ -54,7 +54,7 @@ def solve_local(lib, lps, method="hsd", device=0, mode=0, nstreams=4):
         for k in ("A", "b", "c", "x", "y"):
             setattr(d, k, arrs[k].ctypes.data_as(_dp))
     if lps:
-        lib.vbk_solve_batch(0 if method == "hsd" else 1, device, mode, len(lps), descs, nstreams)
+        lib.vbk_solve_batch({"hsd": 0, "intpt": 1, "hsdls": 2}[method], device, mode, len(lps), descs, nstreams)
     return [dict(status=int(d.status), iterations=int(d.iterations), primal_obj=float(d.primal_obj),
                  dual_obj=float(d.dual_obj), seconds=float(d.seconds), x=a["x"], y=a["y"])
             for d, a in zip(descs, keep)]

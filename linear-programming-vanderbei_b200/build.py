@@ -54,7 +54,7 @@ def build_product(force=False, verbose_ptxas=False) -> Path:
         if verbose_ptxas:
             cmd[1:1] = ["-Xptxas", "-v"]
         run(cmd)
-    for meth in ("hsd", "intpt"):
+    for meth in ("hsd", "hsdls", "intpt"):
         shim = PKG / f"libvbkkt_{meth}.so"
         src = CSRC / f"shim_solver_{meth}.c"
         if force or _newer(shim, [src, out]):

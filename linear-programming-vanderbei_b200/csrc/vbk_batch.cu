@@ -68,6 +68,8 @@ extern "C" int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp
             const auto t0 = std::chrono::steady_clock::now();
             d.status = method == 0
                 ? solver_hsd(device, mode, d.m, d.n, d.nz, d.iA, d.kA, d.A, d.b, d.c, d.f, d.x, d.y, nullptr)
+                : method == 2
+                ? solver_hsdls(device, mode, d.m, d.n, d.nz, d.iA, d.kA, d.A, d.b, d.c, d.f, d.x, d.y, nullptr)
                 : solver_intpt(device, mode, d.m, d.n, d.nz, d.iA, d.kA, d.A, d.b, d.c, d.f, d.x, d.y, nullptr);
             d.iterations = last_thread_iterations();
             d.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

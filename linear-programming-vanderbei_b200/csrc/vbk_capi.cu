@@ -146,6 +146,14 @@ int vbk_solver_hsd(int m, int n, int nz, int* iA, int* kA, double* A, double* b,
     std::free(w); std::free(z);       // the reference's plugins free these (hsd.c:290-291)
     return st;
 }
+int vbk_solver_hsdls(int m, int n, int nz, int* iA, int* kA, double* A, double* b, double* c, double f,
+                     double* x, double* y, double* w, double* z)
+{
+    read_env_once();
+    int st = solver_hsdls(g_device, g_mode, m, n, nz, iA, kA, A, b, c, f, x, y, nullptr);
+    std::free(w); std::free(z);       // hsdls.c:273-274
+    return st;
+}
 int vbk_solver_intpt(int m, int n, int nz, int* iA, int* kA, double* A, double* b, double* c, double f,
                      double* x, double* y, double* w, double* z)
 {
@@ -161,6 +169,7 @@ int vbk_solve_lp(int method, int device, int mode, int m, int n, int nz, const i
 {
     SolveProfile p;
     int st = method == 0 ? solver_hsd(device, mode, m, n, nz, iA, kA, A, b, c, f, x, y, prof ? &p : nullptr)
+           : method == 2 ? solver_hsdls(device, mode, m, n, nz, iA, kA, A, b, c, f, x, y, prof ? &p : nullptr)
                          : solver_intpt(device, mode, m, n, nz, iA, kA, A, b, c, f, x, y, prof ? &p : nullptr);
     if (prof) {
         prof->total_s = p.total_s; prof->setup_s = p.setup_s; prof->factor_s = p.factor_s; prof->solve_s = p.solve_s;

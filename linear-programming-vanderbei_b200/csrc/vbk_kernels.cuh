@@ -403,6 +403,51 @@ static __global__ void k_ratio_test(int n, const double* __restrict__ dx, const 
         if (b > 0.0) atomicMax(slot, double_to_bits(b));
     }
 }
+// Long-step variant (reference src/ipo/hsdls.c): per-component step length from the quadratic
+//   (x + t dx)(z + t dz) >= (1 - beta) mu(t)      (linesearch, hsdls.c:296-336, same expression shapes => same roundings)
+__device__ __forceinline__ double vbk_linesearch(double xj, double zj, double dxj, double dzj, double beta, double delta, double mu)
+{
+    const double a = dxj * dzj;
+    const double b = zj * dxj + xj * dzj + (1 - beta) * (1 - delta) * mu;
+    const double c = xj * zj - (1 - beta) * mu;
+    const double d = b * b - 4 * a * c;
+    if (a == 0.0) return -c / b;
+    if (a > 0) {
+        if (b < 0) return d >= 0 ? 2 * c / (-b + sqrt(d)) : HUGE_VAL;
+        return HUGE_VAL;
+    }
+    if (b < 0) return 2 * c / (-b + sqrt(d));
+    return (-b - sqrt(d)) / (2 * a);
+}
+// doubles -> unsigned keys with the same order (negative values included), for atomicMin
+__device__ __forceinline__ unsigned long long vbk_order_key(double v) {
+    const unsigned long long b = double_to_bits(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double vbk_order_unkey(unsigned long long k) {
+    return bits_to_double((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k);
+}
+// hsdls.c:222-236 folds theta = MIN(theta, linesearch(...)) over the components with the macro MIN(a,b) = a<b ? a : b:
+// a NaN value REPLACES the running minimum and is itself replaced by the next value.  The fold therefore equals the
+// minimum over the entries after the last NaN.  Pass 1 stores the values and finds the last NaN, pass 2 takes the minimum
+// behind it (both order-free), the host finishes the fold with the initial 1.0 and the (phi, psi) term.
+static __global__ void k_linesearch(int n, int base, const double* __restrict__ x, const double* __restrict__ z,
+                                    const double* __restrict__ dx, const double* __restrict__ dz, double beta, double delta,
+                                    double mu, double* __restrict__ vals, int* __restrict__ lastnan)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const double v = vbk_linesearch(x[t], z[t], dx[t], dz[t], beta, delta, mu);
+        vals[base + t] = v;
+        if (v != v) atomicMax(lastnan, base + t);
+    }
+}
+static __global__ void k_min_after(int total, const double* __restrict__ vals, const int* __restrict__ lastnan,
+                                   unsigned long long* __restrict__ slot)
+{
+    const int first = *lastnan + 1;
+    for (int t = first + blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+        atomicMin(slot, vbk_order_key(vals[t]));
+}
 // x += theta*dx; z += theta*dz  (hsd.c:265-268)
 static __global__ void k_step2(int n, double theta, const double* __restrict__ dx, const double* __restrict__ dz,
                         double* __restrict__ x, double* __restrict__ z)

@@ -145,6 +145,29 @@ void show_small_problem(int m, int n, const int* kA, const int* iA, const double
 
 }  // namespace
 
+// hsdls.c:296-336 on the host (the (phi, psi) component) and the inverse of the device's order key
+static double ls_host(double xj, double zj, double dxj, double dzj, double beta, double delta, double mu)
+{
+    const double a = dxj * dzj;
+    const double b = zj * dxj + xj * dzj + (1 - beta) * (1 - delta) * mu;
+    const double c = xj * zj - (1 - beta) * mu;
+    const double d = b * b - 4 * a * c;
+    if (a == 0.0) return -c / b;
+    if (a > 0) {
+        if (b < 0) return d >= 0 ? 2 * c / (-b + std::sqrt(d)) : HUGE_VAL;
+        return HUGE_VAL;
+    }
+    if (b < 0) return 2 * c / (-b + std::sqrt(d));
+    return (-b - std::sqrt(d)) / (2 * a);
+}
+static double ls_unkey(unsigned long long k)
+{
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double v;
+    std::memcpy(&v, &b, 8);
+    return v;
+}
+
 static int g_itnlim = 200;
 void set_iteration_limit(int itnlim) { g_itnlim = itnlim > 0 ? itnlim : 200; }
 
@@ -162,8 +185,11 @@ void set_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, d
     g_cap.iter = iter; g_cap.E = E; g_cap.D = D; g_cap.ry = rhs_y; g_cap.rx = rhs_x; g_cap.sy = sol_y; g_cap.sx = sol_x;
 }
 
-int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
-               const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof)
+// METHOD = hsd (reference src/ipo/hsd.c) and, with longstep, METHOD = hsdls (src/ipo/hsdls.c): the same homogeneous
+// self-dual iteration; hsdls keeps delta = 2(1 - beta) constant instead of alternating predictor / corrector, takes the
+// step length from a per-component quadratic line search, runs up to 600 iterations and has its own status rules.
+static int solver_hsd_impl(bool longstep, int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
+                           const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof)
 {
     const bool timed = prof != nullptr;
     auto t_begin = std::chrono::steady_clock::now();
@@ -173,7 +199,7 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
     cudaStream_t st = W.st;
     int status = 5;
 
-    if (m < 20 && n < 20 && !t_quiet) show_small_problem(m, n, kA, iA, A, b, c);
+    if (!longstep && m < 20 && n < 20 && !t_quiet) show_small_problem(m, n, kA, iA, A, b, c);   // hsd.c:70-95 only
 
     W.fill(W.x, n, 1.0); W.fill(W.z, n, 1.0); W.fill(W.w, m, 1.0); W.fill(W.y, m, 1.0);
     double phi = 1.0, psi = 1.0;
@@ -187,21 +213,27 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
     VBK_LOG_FLUSH();
     if (timed) { cudaStreamSynchronize(st); prof->setup_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); }
 
+    const double beta = 0.80, delta_ls = 2 * (1 - beta);                          // hsdls.c:112-113
+    const int itnlim = longstep ? (g_itnlim == 200 ? 600 : g_itnlim) : g_itnlim; // MAX_ITER: hsd.c:25, hsdls.c:25
+    DevArray<double> lsvals;
+    DevArray<int> lsnan;
+    if (longstep) { lsvals.alloc((size_t)n + m); lsnan.alloc(1); }
     int iter;
-    for (iter = 0; iter < g_itnlim; iter++) {
+    for (iter = 0; iter < itnlim; iter++) {
         double d[4];
         {
             DotJob jobs[4] = {{W.z.p, W.x.p, n}, {W.w.p, W.y.p, m}, {W.c.p, W.x.p, n}, {W.b.p, W.y.p, m}};
             W.la.dots_dev(jobs, 4, d);
         }
         const double mu = (d[0] + d[1] + phi * psi) / (n + m + 1);              // hsd.c:136
-        const double delta = (iter % 2 == 0) ? 0.0 : 1.0;
+        const double delta = longstep ? delta_ls : ((iter % 2 == 0) ? 0.0 : 1.0);
         const double primal_obj = d[2], dual_obj = d[3];
 
-        if (mu < 1.0e-12) {                                                     // hsd.c:155-176
-            if (phi > psi) { status = 0; break; }
+        if (mu < 1.0e-12) {                                                     // hsd.c:155-176, hsdls.c:134-153
+            if (longstep ? (phi > 1.0e-12) : (phi > psi)) { status = 0; break; }
             else if (dual_obj < 0.0) { status = 2; break; }
             else if (primal_obj > 0.0) { status = 4; break; }
+            else if (longstep) { status = 7; break; }
             else { VBK_LOG("Trouble in river city \n"); status = 4; break; }
         }
 
@@ -266,11 +298,41 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
         W.launches(4);
         const double dpsi = delta * mu / phi - psi - (psi / phi) * dphi;
 
-        // step length (hsd.c:248-259)
-        double theta = W.ratio_max();
-        if (theta < -dphi / phi) theta = -dphi / phi;
-        if (theta < -dpsi / psi) theta = -dpsi / psi;
-        theta = VMIN(0.95 / theta, 1.0);
+        double theta;
+        if (!longstep) {
+            // step length (hsd.c:248-259)
+            theta = W.ratio_max();
+            if (theta < -dphi / phi) theta = -dphi / phi;
+            if (theta < -dpsi / psi) theta = -dpsi / psi;
+            theta = VMIN(0.95 / theta, 1.0);
+        } else {
+            // step length (hsdls.c:222-241): MIN-fold of the per-component line searches, see k_linesearch
+            const int minus1 = -1;
+            const unsigned long long top = ~0ull;
+            VBK_CUDA(cudaMemcpyAsync(lsnan.p, &minus1, sizeof(int), cudaMemcpyHostToDevice, st));
+            VBK_CUDA(cudaMemcpyAsync(W.slot.p, &top, 8, cudaMemcpyHostToDevice, st));
+            VBK_LAUNCH(k_linesearch, W.g(n), kVecThreads, 0, st, n, 0, W.x.p, W.z.p, W.dx.p, W.dz.p, beta, delta, mu, lsvals.p, lsnan.p);
+            VBK_LAUNCH(k_linesearch, W.g(m), kVecThreads, 0, st, m, n, W.y.p, W.w.p, W.dy.p, W.dw.p, beta, delta, mu, lsvals.p, lsnan.p);
+            VBK_LAUNCH(k_min_after, W.g(n + m), kVecThreads, 0, st, n + m, lsvals.p, lsnan.p, W.slot.p);
+            W.launches(3);
+            int lastnan = -1;
+            unsigned long long key = top;
+            VBK_CUDA(cudaMemcpyAsync(W.pin_slot, W.slot.p, 8, cudaMemcpyDeviceToHost, st));
+            VBK_CUDA(cudaMemcpyAsync(&lastnan, lsnan.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            VBK_CUDA(cudaStreamSynchronize(st));
+            std::memcpy(&key, W.pin_slot, 8);
+            theta = 1.0;
+            if (lastnan == n + m - 1) theta = std::nan("");
+            else if (key != top) {
+                const double vmin = ls_unkey(key);
+                theta = lastnan >= 0 ? vmin : (theta < vmin ? theta : vmin);
+            }
+            {   // the (phi, psi) component, hsdls.c:233, on the host in the reference's own expression shapes
+                const double v = ls_host(phi, psi, dphi, dpsi, beta, delta, mu);
+                theta = theta < v ? theta : v;
+            }
+            if (theta < 1.0) theta *= 0.9999;
+        }
 
         VBK_LAUNCH(k_step2, W.g(n), kVecThreads, 0, st, n, theta, W.dx.p, W.dz.p, W.x.p, W.z.p);
         VBK_LAUNCH(k_step2, W.g(m), kVecThreads, 0, st, m, theta, W.dy.p, W.dw.p, W.y.p, W.w.p);
@@ -290,6 +352,17 @@ int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const 
         prof->total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     }
     return status;
+}
+
+int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
+               const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof)
+{
+    return solver_hsd_impl(false, device, mode, m, n, nz, iA, kA, A, b, c, f, x, y, prof);
+}
+int solver_hsdls(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
+                 const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof)
+{
+    return solver_hsd_impl(true, device, mode, m, n, nz, iA, kA, A, b, c, f, x, y, prof);
 }
 
 int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,

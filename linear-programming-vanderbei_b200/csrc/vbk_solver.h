@@ -1,4 +1,4 @@
-// vbk_solver.h -- device-resident METHOD plugins (hsd / intpt), see vbk_solver.cu.
+// vbk_solver.h -- device-resident METHOD plugins (hsd / hsdls / intpt), see vbk_solver.cu.
 #pragma once
 
 namespace vbk {
@@ -12,9 +12,12 @@ struct SolveProfile {
     double narth = 0;
 };
 
-// status: 0 optimal, 2 primal infeasible, 4 dual infeasible, 5 iteration limit (main.c:21-30)
+// status: 0 optimal, 2 primal infeasible, 4 dual infeasible, 5 iteration limit, 7 numerical problem (hsdls) (main.c:21-30)
 int solver_hsd(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
                const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof);
+// METHOD = hsdls (reference src/ipo/hsdls.c:37): homogeneous self-dual, long steps with a per-component line search
+int solver_hsdls(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
+                 const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof);
 int solver_intpt(int device, int mode, int m, int n, int nz, const int* iA, const int* kA, const double* A,
                  const double* b, const double* c, double f, double* x, double* y, SolveProfile* prof);
 

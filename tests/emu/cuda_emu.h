@@ -85,6 +85,11 @@ inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v)
     while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 inline double atomicAdd(double* p, double v) {
     unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
     unsigned long long old = __atomic_load_n(q, __ATOMIC_SEQ_CST), nw;

@@ -138,6 +138,21 @@ def check_full_solve(vbkkt, lib, lp, method, want_bits=True):
     return st
 
 
+def check_hsdls(vbkkt, lib, lp):
+    """METHOD = hsdls (reference src/ipo/hsdls.c:37-336) against the committed output of the compiled reference
+    (tests/golden/hsdls/, made by tests/golden/make_hsdls.py): same status, byte-identical log, bit-equal x and y."""
+    z = np.load(H.GOLDEN / "hsdls" / f"{lp.name}.npz")
+    st, log, x, y, _ = H.solve_via(vbkkt, lib, lp, "hsdls")
+    assert st == int(z["status"])
+    exp = str(z["log"])
+    a, b = log.splitlines(), exp.splitlines()
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert u == v, f"{lp.name} hsdls: first differing log line {i}:\n got {u!r}\n exp {v!r}"
+    assert len(a) == len(b), f"{lp.name} hsdls: {len(a)} lines, expected {len(b)}"
+    assert np.array_equal(x, z["x"]) and np.array_equal(y, z["y"])
+    return st
+
+
 def north_star_tolerances(lp, method, x, y, status, log, iter_slack=1):
     """The tolerance form of parity (BASELINE.json north_star): objective 1e-8 relative,
     infeasibilities 1e-7, iteration count +-1, same status."""

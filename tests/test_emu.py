@@ -87,3 +87,11 @@ def test_emu_full_solve_intpt_afiro(vbkkt, emu_lib):
     lp = H.load_fixture("afiro")
     assert P.check_full_solve(vbkkt, emu_lib, lp, "intpt") == 0
     assert len(H.iteration_lines(str(lp.extra["intpt_log"]))) == 25
+
+
+@pytest.mark.parametrize("name", ["afiro"])
+def test_emu_full_solve_hsdls(vbkkt, emu_lib, name):
+    """the long-step METHOD (hsdls.c) end to end through the emulated kernels -- per-component line
+    search (hsdls.c:296-336) with the reference's MIN-fold semantics, constant delta, its own status rules -- prints
+    the compiled reference's log byte for byte and returns bit-equal x and y."""
+    assert P.check_hsdls(vbkkt, emu_lib, H.load_fixture(name)) == 0

@@ -75,6 +75,14 @@ def test_intpt_log_and_solution_match_reference(vbkkt, gpu_lib, name):
         assert len(H.iteration_lines(str(lp.extra["intpt_log"]))) == 25
 
 
+@pytest.mark.parametrize("name", ["afiro", "adlittle", "blend", "sc50a", "sc50b", "sc105", "share2b", "kb2", "israel", "stocfor1",
+                                  "scsd1", "e226", "bandm", "sctap1", "25fv47"])
+def test_hsdls_log_and_solution_match_reference(vbkkt, gpu_lib, name):
+    """METHOD = hsdls (src/ipo/hsdls.c:37-336) device-resident; oracle = the compiled reference's committed
+    output (no golden logs exist for it): byte-identical log, bit-equal x and y."""
+    P.check_hsdls(vbkkt, gpu_lib, H.load_fixture(name))
+
+
 def test_north_star_tolerances_hold(vbkkt, gpu_lib):
     for name in ("afiro", "25fv47"):
         lp = H.load_fixture(name)

@@ -19,13 +19,13 @@ def test_library_exports_every_declared_symbol(product_lib):
     names -= {"defined", "C"}
     decl = {n for n in names if re.search(r"\b(void|int|double|long|char|vbk_kkt)\b[\s\*]+" + n + r"\s*\(", header)}
     assert {"ldltfac", "forwardbackward", "smx", "atnum", "dotprod", "maxv", "inv_clo", "inv_num", "solve",
-            "vbk_solver_hsd", "vbk_solver_intpt", "vbk_kkt_create", "vbk_solve_lp"} <= decl
+            "vbk_solver_hsd", "vbk_solver_hsdls", "vbk_solver_intpt", "vbk_kkt_create", "vbk_solve_lp"} <= decl
     for n in sorted(decl):
         assert hasattr(product_lib, n), f"libvbkkt.so does not export {n}"
 
 
 def test_solver_shims_export_solver(product_lib, vbkkt):
-    for meth in ("hsd", "intpt"):
+    for meth in ("hsd", "hsdls", "intpt"):
         lib = C.CDLL(str(vbkkt.PKG_DIR / f"libvbkkt_{meth}.so"))
         assert hasattr(lib, "solver")
 
