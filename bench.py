@@ -379,10 +379,42 @@ def run_rowblock(a, vb, lib, rank, local_rank, world):
         sig = torch.zeros(ops.cols_per, dtype=torch.float64, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-        def step():
+        def step_eager():
             return ops.step(lx, ly, rho, sig)      # hsd.c:182-195: A x, A^T y, 4 dot products, 2 max-norms
         for _ in range(warm):
-            d, mx = step()
+            d, mx = step_eager()
+        # The step is a dozen small launches and three collectives: issued one by one from Python it is bound by launch
+        # latency, not by the GPU.  Capture it once in a CUDA graph (NCCL collectives included) and replay that.
+        graph, graphed = None, "eager"
+        if not a.no_graph:
+            try:
+                torch.cuda.synchronize()
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.barrier()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        step_eager()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    gd, gmx = ops.step(lx, ly, rho, sig, overlap=False)
+                graph.replay()
+                torch.cuda.synchronize()
+                graphed = "cuda graph (one replay per step)"
+            except Exception as e:                       # capture not possible with this torch/NCCL: stay eager, say so
+                graph, graphed = None, f"eager (graph capture failed: {type(e).__name__})"
+                torch.cuda.synchronize()
+
+        def step():
+            if graph is not None:
+                graph.replay()
+                return gd, gmx
+            return step_eager()
+        d, mx = step()
         # parity: the distributed products against a host computation of the same sums
         import scipy.sparse as sp
         Acsr = sp.csc_matrix((lp.A, lp.iA, lp.kA), shape=(lp.m, lp.n)).tocsr()
@@ -427,7 +459,7 @@ def run_rowblock(a, vb, lib, rank, local_rank, world):
                    "dtype": "f64", "data": "synthetic multicommodity LP (generator seed 1)",
                    "config": {"workload": f"BASELINE config 5: multicommodity R={a.grid} K={a.commodities}: m={lp.m} n={lp.n} nz={lp.nz}; step = A x + A^T y "
                                           "(all-gather + row-block SpMV each, both all-gathers in flight together) + 4 dot products + 2 max-norms (ONE 48-byte all-gather)",
-                              "l2": "flushed between timed steps (256 MiB write)",
+                              "l2": "flushed between timed steps (256 MiB write)", "launch": graphed,
                               "parallelism": f"row blocks over {world} rank(s); NCCL all-gather of x, y and of the 6 partial scalars"},
                    "e2e": {"value": total_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
                            "h2d_bytes_per_step": int(8 * (ops.c1 - ops.c0 + ops.r1 - ops.r0)),
@@ -471,6 +503,7 @@ def main():
                     help="batch workload: arithmetic mode (fast: tolerance parity, all LPs checked optimal + one strict sample)")
     ap.add_argument("--batch-steps", type=int, default=1)
     ap.add_argument("--rowblock-steps", type=int, default=20)
+    ap.add_argument("--no-graph", action="store_true", help="row-block workload: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="batch workload: LPs per GPU per step (default: 2 per solver stream, at least 8)")
     ap.add_argument("--batch-m", type=int, default=2000)
     ap.add_argument("--batch-n", type=int, default=4000)

@@ -157,22 +157,26 @@ class RowBlockOps:
         return out.clone()       # the reduction buffer is reused by the next call: hand out a copy
 
     # -- one interior-point residual step, collectives overlapped -------------------------------------
-    def step(self, x_local, y_local, rho, sig):
+    def step(self, x_local, y_local, rho, sig, overlap=True):
         """rho = (A x)[rows], sig = (A^T y)[cols] and the six scalars hsd.c:182-195 needs from them --
         x.sig, y.rho, rho.rho, sig.sig (sums) and max|rho|, max|sig| -- with as little exposed communication as the
         partition allows: both all-gathers are issued at once (NCCL's own stream) and each SpMV waits only for its own
         operand, and the six partial scalars of all ranks travel in ONE small all-gather; every rank then adds (resp.
         maximises) them in rank order, so all ranks hold bit-identical results.  Returns (sums[4], maxes[2])."""
-        if self.world > 1:
+        hy = None
+        if self.world > 1 and overlap:
             hx = self.dist.all_gather_into_tensor(self.full_x, x_local, group=self.group, async_op=True)
             hy = self.dist.all_gather_into_tensor(self.full_y, y_local, group=self.group, async_op=True)
             hx.wait()
+        elif self.world > 1:                 # stream-ordered (CUDA graph capture): the collectives sit on the current stream
+            self.dist.all_gather_into_tensor(self.full_x, x_local, group=self.group)
+            self.dist.all_gather_into_tensor(self.full_y, y_local, group=self.group)
         else:
             self.full_x.copy_(x_local); self.full_y.copy_(y_local)
         ptr, idx, val, _ = self.rowblk
         self.lib.vbk_spmv_rows_dev(self.r1 - self.r0, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(),
                                    self.full_x.data_ptr(), rho.data_ptr(), self._stream())
-        if self.world > 1:
+        if hy is not None:
             hy.wait()
         ptr, idx, val, _ = self.colblk
         self.lib.vbk_spmv_rows_dev(self.c1 - self.c0, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(),
