@@ -70,16 +70,30 @@ static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArg
         if (r >= a.nclaim) break;
         double acc = a.z[r];                         // right-hand side entry, written before the launch
         const int rb = a.rowptr[r], re = a.rowptr[r + 1];
+        // the row's entries 32 at a time; the static part of the NEXT batch (column, L value) is fetched while this one
+        // waits for its columns and runs its chain
+        int nj = -1;
+        double nl = 0.0;
+        if (rb + lane < re) { nj = a.rj[rb + lane]; nl = a.L[a.rk[rb + lane]]; }
         for (int t0 = rb; t0 < re; t0 += 32) {
-            const int t = t0 + lane;
-            double p = 0.0;        // an unmarked column contributes nothing (ldlt.c:455); x - (+0.0) == x
-            if (t < re) {
-                const int j = a.rj[t];
-                const double l = a.L[a.rk[t]];
-                while (vbk_ld_volatile(&a.done[j]) == 0) __nanosleep(20);
-                __threadfence();
-                if (a.mark[j]) p = l * __ldcg(&a.z[j]);
+            const int j = nj;
+            const double l = nl;
+            nj = -1; nl = 0.0;
+            if (t0 + 32 + lane < re) { nj = a.rj[t0 + 32 + lane]; nl = a.L[a.rk[t0 + 32 + lane]]; }
+            // Wait for the batch's columns.  Every lane looks at its flag once; then only the lane with the smallest
+            // unfinished column spins (a row of the dense tail waits for the next 32 columns of the chain: 32 spinning
+            // lanes in each of thousands of warps would saturate the L2 with polls), the others re-check when it is done.
+            unsigned pending = __ballot_sync(0xffffffffu, j >= 0 && vbk_ld_volatile(&a.done[j]) == 0);
+            while (pending) {
+                const int first = __ffs(pending) - 1;
+                if (lane == first) { while (vbk_ld_volatile(&a.done[j]) == 0) __nanosleep(20); }
+                __syncwarp();
+                pending = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && lane != first && vbk_ld_volatile(&a.done[j]) == 0);
             }
+            // z[j] is read only after its flag has been seen set (control dependency) and bypasses L1; the writer
+            // released z before raising the flag
+            double p = 0.0;        // an unmarked column contributes nothing (ldlt.c:455); x - (+0.0) == x
+            if (j >= 0 && a.mark[j]) p = l * __ldcg(&a.z[j]);
             sp[lane] = p;
             __syncwarp();
             if (lane == 0) acc = chain_sub(acc, sp, (re - t0 < 32) ? (re - t0) : 32);   // z[row] -= AAt[k]*beta
@@ -89,7 +103,7 @@ static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArg
             if (a.mark[r]) a.z[r] = acc;
             else if (fabs(acc) > eps) { a.z[r] = acc; a.counters[C_CONSISTENT] = 0; }
             else a.z[r] = 0.0;
-            __threadfence();
+            vbk_fence_release();
             atomicExch(&a.done[r], 1);
         }
         __syncwarp();

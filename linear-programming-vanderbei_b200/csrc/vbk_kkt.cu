@@ -131,7 +131,7 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
     rk_sig_.upload(sym_.rk_sig, stream_); rj_sig_.upload(sym_.rj_sig, stream_);
     rk_asc_.upload(sym_.rk_asc, stream_); rj_asc_.upload(sym_.rj_asc, stream_);
 
-    L_.alloc((size_t)lnz + 2);          // + 2: the strict factor's bulk copies start and end at even entries
+    L_.alloc((size_t)lnz + 160);        // padding: the strict factor kernel's unconditional row loads may run past the last column
     diag_.alloc(N); mark_.alloc(N);
     counters_.alloc(C_COUNT); scal_.alloc(S_COUNT); bits_.alloc(S_COUNT);
     z_.alloc(N); xk_.alloc(n); yk_.alloc(m); r_.alloc(m); s_.alloc(n);
@@ -218,6 +218,7 @@ void Kkt::launch_factor_pipe(int ntasks, bool timed)
     pa.winptr = winptr_.p; pa.nblk = sym_.nblk; pa.rowblk = sym_.rowblk; pa.slice_row0 = sym_.slice_row0;
     pa.col_pub = col_pub_.p; pa.col_done = col_done_.p; pa.task_max = task_max_.p;
     pa.counters = counters_.p; pa.scal_bits = bits_.p; pa.epsnum = 0.0;        // _EPSNUM, ldlt.c:29
+    pa.two_pass = std::getenv("VBK_ONE_PASS") ? 0 : 1;
     if (std::getenv("VBK_PROF") && !prof_.p) { prof_.alloc(16); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 128, stream_)); }
     pa.prof = prof_.p;
     if (pa.prof && !trace_.p) trace_.alloc((size_t)N * 8);

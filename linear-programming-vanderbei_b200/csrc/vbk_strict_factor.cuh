@@ -58,6 +58,7 @@ struct PipeArgs {
     int* col_done;      // [N] 1 once L[:,j], diag[j] and mark[j] are final
     double* task_max;   // [ntasks] max|undivided entry| of a non-owner slice
     int* counters; const unsigned long long* scal_bits; double epsnum;
+    int two_pass;       // 1: stage the ready contributors of a group before waiting for the others
     // optional [16] cycle counters ($VBK_PROF), lane 0 of each role: 0 consumer waits for a stage, 1 consumer adds,
     // 2 producer waits for a free slot, 3 static structure + zero fill, 4 waits for the contributors' columns,
     // 5 fence + lij, dj, 6 products, 7 publish; 8 claim + task setup, 9 epilogue up to col_pub / pivot wait,
@@ -99,16 +100,18 @@ static __global__ void k_pipe_reset(int N, int* __restrict__ col_pub, int* __res
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[C_NEXT] = 0; counters[C_NDEP] = 0; }
 }
 
-// Products of one ring stage, kept lean: a producer warp is bound by its own instruction stream (one warp issues an
-// instruction every few cycles at best), so what counts is instructions per row.
+// Products of (a subset of) one ring stage.  A producer warp is bound by its own instruction stream and by the round
+// trips it exposes, so: few instructions per row, many loads in flight, no shared-memory load behind a store.
+//  * lane q of the warp holds contributor q's record (w = lij*dj, kb = first entry of column j in the rows of the task,
+//    len = how many); rows get it by warp shuffle.
 //  * "full" rows -- the contributor holds every row of the task, the rule in the dense tail -- need neither row indices
-//    nor a zero fill: slot = position.  Eight rows per batch: eight loads in flight, then eight products.
+//    nor a zero fill (slot = position): all full rows of the stage are loaded in ONE batch (one exposed round trip).
 //  * the other rows are zero-filled (+0.0 where a contributor has no entry) and scattered through the block's row -> slot
 //    map (BLK) or a branch-free binary search over the task's sorted rows (whole columns), eight rows per batch; all
-//    look-ups of a batch come before its first store (a store would fence off the shared-memory loads behind it).
-// fullm / partm / zerom: one bit per contributor of the stage (warp-uniform).
+//    look-ups of a batch come before its first store.
+// fullm / partm / zerom: one bit per contributor of the stage to handle in this call (warp-uniform).
 template <int NCH, bool BLK>
-__device__ __forceinline__ void pipe_products(const PipeArgs& a, const PipeMeta* __restrict__ mp, double* __restrict__ tp,
+__device__ __forceinline__ void pipe_products(const PipeArgs& a, double w, int kb, int len, double* __restrict__ tp,
                                               unsigned fullm, unsigned partm, unsigned zerom,
                                               const int* __restrict__ blockmap, const int* __restrict__ rows,
                                               int cnt, int bs, int lane)
@@ -117,27 +120,32 @@ __device__ __forceinline__ void pipe_products(const PipeArgs& a, const PipeMeta*
     constexpr int kSteps = (NCH == 1) ? 5 : (NCH == 2 ? 6 : 7);    // log2(cap)
     const double* Lp = a.L + lane;
     double* tpl = tp + lane;
-    if (fullm) {
-        constexpr int FB = 8 / (NCH > 2 ? 2 : 1);
-#pragma unroll 1
-        for (int q0 = 0; q0 < kPipeQ; q0 += FB) {
-            double wv[FB], val[FB][NCH];
+    // full rows, compacted: up to FB of them per batch, all loads of a batch in flight together.  The loads are
+    // UNCONDITIONAL (a predicated load keeps its predicate alive until the value is used, and with seven predicate
+    // registers the compiler then serialises a batch six rows at a time); a slot past the end of the list repeats the
+    // last row (never a fixed dummy address: thousands of warps reading one line make it a hot spot in the L2), lanes
+    // beyond the task's rows read into the next column or the padding behind L.
+    {
+        constexpr int FB = 16 / NCH;
+        unsigned todo = fullm;
+        while (todo) {
+            int qs[FB];
+            double val[FB][NCH];
+            int nrows = 0, qlast = 0;
 #pragma unroll
             for (int u = 0; u < FB; ++u) {
-                if ((fullm >> (q0 + u)) & 1u) {
-                    const PipeMeta m = mp[q0 + u];
-                    wv[u] = m.w;
+                if (todo) { qlast = __ffs(todo) - 1; todo &= todo - 1; ++nrows; }
+                qs[u] = qlast;
+                const int kbq = __shfl_sync(0xffffffffu, kb, qlast);
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) val[u][c] = (lane + 32 * c < cnt) ? __ldcg(Lp + m.kb + 32 * c) : 0.0;
-                }
+                for (int c = 0; c < NCH; ++c) val[u][c] = __ldcg(Lp + kbq + 32 * c);
             }
 #pragma unroll
             for (int u = 0; u < FB; ++u) {
-                if ((fullm >> (q0 + u)) & 1u) {
+                const double wq = __shfl_sync(0xffffffffu, w, qs[u]);
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c)
-                        if (lane + 32 * c < cnt) tpl[(q0 + u) * cap + 32 * c] = wv[u] * val[u][c];     // lij_dj*AAt[kk], ldlt.c:583
-                }
+                for (int c = 0; c < NCH; ++c)
+                    if (u < nrows && lane + 32 * c < cnt) tpl[qs[u] * cap + 32 * c] = wq * val[u][c];   // lij_dj*AAt[kk], ldlt.c:583
             }
         }
     }
@@ -151,7 +159,7 @@ __device__ __forceinline__ void pipe_products(const PipeArgs& a, const PipeMeta*
         }
         __syncwarp();
     }
-    constexpr int QB = (NCH == 1) ? 4 : (NCH == 2 ? 2 : 1);
+    constexpr int QB = (NCH == 1) ? 8 : (NCH == 2 ? 4 : 2);
     while (partm) {
         int qs[QB], lens[QB], ri[QB][NCH], slot[QB][NCH];
         double wv[QB], val[QB][NCH];
@@ -159,22 +167,25 @@ __device__ __forceinline__ void pipe_products(const PipeArgs& a, const PipeMeta*
         for (int u = 0; u < QB; ++u) {
             qs[u] = partm ? __ffs(partm) - 1 : -1;
             partm &= partm - 1;
-            const PipeMeta m = mp[qs[u] < 0 ? 0 : qs[u]];
-            lens[u] = qs[u] < 0 ? 0 : m.len;
-            wv[u] = m.w;
+            const int q = qs[u] < 0 ? 0 : qs[u];
+            const int kbq = __shfl_sync(0xffffffffu, kb, q);
+            const int lq = __shfl_sync(0xffffffffu, len, q);
+            wv[u] = __shfl_sync(0xffffffffu, w, q);
+            lens[u] = qs[u] < 0 ? 0 : lq;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int e = lane + 32 * c;
-                val[u][c] = 0.0;
-                ri[u][c] = bs;
-                if (e < lens[u]) { val[u][c] = __ldcg(Lp + m.kb + 32 * c); ri[u][c] = a.iL[m.kb + e]; }
+                const int idx = kbq + ((e < lens[u]) ? e : 0);        // unconditional loads, see above
+                val[u][c] = __ldcg(a.L + idx);
+                ri[u][c] = a.iL[idx];
             }
         }
 #pragma unroll
         for (int u = 0; u < QB; ++u) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                if (BLK) slot[u][c] = blockmap[ri[u][c] - bs];
+                const int e = lane + 32 * c;
+                if (BLK) slot[u][c] = blockmap[(e < lens[u]) ? ri[u][c] - bs : 0];
                 else {
                     int sl = 0;              // rows[] is sorted and holds the row: largest s with rows[s] <= row
 #pragma unroll
@@ -341,36 +352,45 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                     __threadfence_block();
                 }
                 VBK_PTICK(2);
-                // (3) the contributor's column must be final (acquire: the loads below see its final values)
-                if (valid && !flag) {
-                    while (vbk_ld_volatile(&a.col_done[j]) == 0) { __nanosleep(20); vbk_pause(); }
-                    (void)vbk_ld_acquire(&a.col_done[j]);
-                    lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]);
-                }
-                VBK_PTICK(4);
-                {
-                    PipeMeta m;
-                    m.w = lij * dj;                                    // lij_dj, ldlt.c:572
-                    m.kb = kb; m.len = len;
-                    s_meta[st * kPipeQ + lane] = m;
-                    s_l[st * kPipeQ + lane] = lij;
-                }
-                // (4) column end and block range of the next group's contributors
+                // (3) column end and block range of the next group's contributors
                 int nke = 0, nlo = 0, nhi = 0x7fffffff;
                 if (nvalid) {
                     nke = a.kL[nj + 1];
                     if (blk >= 0) { const int* wp = a.winptr + (size_t)nj * wstride; nlo = wp[blk]; nhi = wp[blk + 1]; }
                 }
-                __syncwarp();
-                VBK_PTICK(5);
-                // (5) products
-                {
-                    const bool isfull = valid && cnt > 0 && len == cnt;
-                    const unsigned fullm = __ballot_sync(0xffffffffu, isfull);
-                    const unsigned partm = __ballot_sync(0xffffffffu, valid && len > 0 && !isfull);
-                    if (blk >= 0) pipe_products<NCH, true>(a, s_meta + st * kPipeQ, tp, fullm, partm, ~fullm, blockmap, rows, cnt, bs, lane);
-                    else          pipe_products<NCH, false>(a, s_meta + st * kPipeQ, tp, fullm, partm, ~fullm, blockmap, rows, cnt, bs, lane);
+                VBK_PTICK(4);
+                // (4) products, in two passes: first every contributor whose column was final when the group was
+                //     prepared -- all of them in steady state, all but the youngest child when the task runs ahead of the
+                //     critical path -- then, as its column becomes final, what is left.  When the last child finishes only
+                //     its own rows remain to be staged.
+                const bool isfull = valid && cnt > 0 && len == cnt;
+                const bool ispart = valid && len > 0 && !isfull;
+                if (!a.two_pass && valid && !flag) {
+                    while (vbk_ld_volatile(&a.col_done[j]) == 0) { __nanosleep(20); vbk_pause(); }
+                    (void)vbk_ld_acquire(&a.col_done[j]);
+                    lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]);
+                    flag = 1;
                 }
+                const unsigned readym = __ballot_sync(0xffffffffu, !valid || flag != 0);
+                const unsigned fullm = __ballot_sync(0xffffffffu, isfull);
+                const unsigned partm = __ballot_sync(0xffffffffu, ispart);
+                double w = lij * dj;                                   // lij_dj, ldlt.c:572
+                if (blk >= 0) pipe_products<NCH, true>(a, w, kb, len, tp, fullm & readym, partm & readym, ~fullm, blockmap, rows, cnt, bs, lane);
+                else          pipe_products<NCH, false>(a, w, kb, len, tp, fullm & readym, partm & readym, ~fullm, blockmap, rows, cnt, bs, lane);
+                VBK_PTICK(5);
+                if (~readym) {
+                    if (valid && !flag) {
+                        while (vbk_ld_volatile(&a.col_done[j]) == 0) { __nanosleep(20); vbk_pause(); }
+                        (void)vbk_ld_acquire(&a.col_done[j]);          // acquire: what is read below is the column's final state
+                        lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]);
+                        w = lij * dj;
+                    }
+                    __syncwarp();
+                    if (blk >= 0) pipe_products<NCH, true>(a, w, kb, len, tp, fullm & ~readym, partm & ~readym, 0u, blockmap, rows, cnt, bs, lane);
+                    else          pipe_products<NCH, false>(a, w, kb, len, tp, fullm & ~readym, partm & ~readym, 0u, blockmap, rows, cnt, bs, lane);
+                }
+                s_meta[st * kPipeQ + lane].w = w;                      // the pivot chain's operands
+                s_l[st * kPipeQ + lane] = lij;
                 VBK_PTICK(6);
                 // (6) next group: entry range, readiness, lij and dj if the column is final already
                 int nkb = nk + 1, nlen = 0, nflag = 1;

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
+#include <string>
 
 namespace vbk {
 
@@ -253,7 +255,54 @@ void Symbolic::analyze(int m_, int n_, const int* kA, const int* iA, const int* 
     dense = 3;  // ldlt.c:814-846 with n1 == 0
 
     const auto t0 = std::chrono::steady_clock::now();
-    order(adj, tier);
+    // $VBK_SYM_CACHE=<directory>: the ordering and the fill pattern (perm, iperm, kAAt, iAAt, denwin, narth) are kept on
+    // disk, keyed by a hash of the matrix pattern (the explicit-fill ordering of the largest synthetic LPs
+    // takes minutes to an hour, for the reference as for any faithful restatement, and depends on the pattern only)
+    std::string cache_file;
+    if (const char* dir = std::getenv("VBK_SYM_CACHE")) {
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&h](const void* p, size_t bytes) {
+            const unsigned char* c = static_cast<const unsigned char*>(p);
+            for (size_t i = 0; i < bytes; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+        };
+        mix(&m, sizeof m); mix(&n, sizeof n); mix(kA, sizeof(int) * ((size_t)n + 1)); mix(iA, sizeof(int) * (size_t)nzA);
+        char name[64];
+        std::snprintf(name, sizeof name, "/vbksym_%d_%d_%016llx.bin", m, n, h);
+        cache_file = std::string(dir) + name;
+    }
+    bool cached = false;
+    if (!cache_file.empty()) {
+        if (FILE* f = std::fopen(cache_file.c_str(), "rb")) {
+            long long hd[8] = {0};
+            double na = 0;
+            if (std::fread(hd, sizeof hd, 1, f) == 1 && std::fread(&na, sizeof na, 1, f) == 1 && hd[0] == 0x314d59534b4256ll &&
+                hd[1] == m && hd[2] == n && hd[3] == nzA && hd[4] == N) {
+                const size_t lnz_ = (size_t)hd[5];
+                perm.resize(N); iperm.resize(N); kL.resize((size_t)N + 1); iL.resize(lnz_);
+                cached = std::fread(perm.data(), sizeof(int), N, f) == (size_t)N && std::fread(iperm.data(), sizeof(int), N, f) == (size_t)N &&
+                         std::fread(kL.data(), sizeof(int), (size_t)N + 1, f) == (size_t)N + 1 &&
+                         std::fread(iL.data(), sizeof(int), lnz_, f) == lnz_ && kL[N] == (int)lnz_;
+                denwin = (int)hd[6]; narth = na;
+                if (!cached) std::fprintf(stderr, "vbkkt: symbolic cache %s is damaged; recomputing\n", cache_file.c_str());
+            }
+            std::fclose(f);
+        }
+    }
+    if (!cached) {
+        order(adj, tier);
+        if (!cache_file.empty()) {
+            const std::string tmp = cache_file + ".tmp";
+            if (FILE* f = std::fopen(tmp.c_str(), "wb")) {
+                const long long hd[8] = {0x314d59534b4256ll, m, n, nzA, N, (long long)kL[N], denwin, pdf};
+                bool ok = std::fwrite(hd, sizeof hd, 1, f) == 1 && std::fwrite(&narth, sizeof narth, 1, f) == 1 &&
+                          std::fwrite(perm.data(), sizeof(int), N, f) == (size_t)N && std::fwrite(iperm.data(), sizeof(int), N, f) == (size_t)N &&
+                          std::fwrite(kL.data(), sizeof(int), (size_t)N + 1, f) == (size_t)N + 1 &&
+                          std::fwrite(iL.data(), sizeof(int), (size_t)kL[N], f) == (size_t)kL[N];
+                ok = (std::fclose(f) == 0) && ok;
+                if (ok) std::rename(tmp.c_str(), cache_file.c_str()); else std::remove(tmp.c_str());
+            }
+        }
+    }
     const auto t1 = std::chrono::steady_clock::now();
     derive(kA, iA, kAt, iAt);
     if (std::getenv("VBK_SYM_STATS"))

@@ -95,3 +95,22 @@ def test_multicommodity_bench_workload(vbkkt, product_lib):
     narth, lnz = bench.MCF_KNOWN[(20, 12)]
     assert k.lnz == lnz and abs(k.narth - narth) <= 1e-3 * narth
     k.close()
+
+
+def test_symbolic_disk_cache_round_trip(vbkkt, emu_lib, tmp_path, monkeypatch):
+    """$VBK_SYM_CACHE: the second analysis of a pattern reads perm / kAAt / iAAt back from disk and yields the same
+    arrays; a different pattern gets its own file."""
+    monkeypatch.setenv("VBK_SYM_CACHE", str(tmp_path))
+    outs = []
+    for name in ("afiro", "afiro", "sc50b"):
+        lp = H.load_fixture(name)
+        kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+        K = vbkkt.KKT(device=-1, lib=emu_lib)
+        K.analyze(lp.n, lp.m, kAt, iAt, At, lp.kA, lp.iA, lp.A)
+        outs.append((K.perm, K.iperm, K.kAAt, K.iAAt, K.denwin, K.narth))
+        K.close()
+    assert len(list(tmp_path.glob("vbksym_*.bin"))) == 2
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    lp = H.load_fixture("afiro")
+    assert np.array_equal(outs[1][0], lp.extra["sym_perm"]) and np.array_equal(outs[1][2], lp.extra["sym_kAAt"])
