@@ -58,7 +58,6 @@ struct PipeArgs {
     int* col_done;      // [N] 1 once L[:,j], diag[j] and mark[j] are final
     double* task_max;   // [ntasks] max|undivided entry| of a non-owner slice
     int* counters; const unsigned long long* scal_bits; double epsnum;
-    int two_pass;       // 1: stage the ready contributors of a group before waiting for the others
     // optional [16] cycle counters ($VBK_PROF), lane 0 of each role: 0 consumer waits for a stage, 1 consumer adds,
     // 2 producer waits for a free slot, 3 static structure + zero fill, 4 waits for the contributors' columns,
     // 5 fence + lij, dj, 6 products, 7 publish; 8 claim + task setup, 9 epilogue up to col_pub / pivot wait,
@@ -276,20 +275,35 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
             // ---- consumer: one register accumulator per row, the reference's additions in the reference's order
 #pragma unroll
             for (int c = 0; c < NCH; ++c) if (lane + 32 * c < cnt) kval[c] = __ldcg(&a.L[p0 + lane + 32 * c]);
-            for (int g = 0; g < ngroups; ++g) {
+            // two ring stages per wait whenever there are two left: one flag check, one release and one pipeline
+            // fill of the shared-memory loads per 64 links instead of per 32
+            for (int g = 0; g < ngroups;) {
                 const int st = g % S;
-                while (vbk_ld_volatile(&full[st]) != g + 1) vbk_pause();
-                __threadfence_block();
+                const bool pair = g + 1 < ngroups;
+                const int st2 = (g + 1) % S;
+                while (vbk_lds_acquire(&full[st]) != g + 1) vbk_pause();
+                if (pair) { while (vbk_lds_acquire(&full[st2]) != g + 2) vbk_pause(); }
                 VBK_PTICK(0);
                 if (tracing && g == 0) a.trace[(size_t)i * 8 + 1] = vbk_globaltimer();
                 const double* tp = tile + (size_t)st * kPipeQ * cap + lane;
+                const double* tp2 = tile + (size_t)st2 * kPipeQ * cap + lane;
+                if (pair) {
 #pragma unroll
-                for (int q = 0; q < kPipeQ; ++q) {
+                    for (int q = 0; q < 2 * kPipeQ; ++q) {
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) acc[c] += tp[q * cap + 32 * c];          // temp[row] += lij_dj*AAt[kk]
+                        for (int c = 0; c < NCH; ++c)
+                            acc[c] += (q < kPipeQ ? tp[q * cap + 32 * c] : tp2[(q - kPipeQ) * cap + 32 * c]);   // temp[row] += lij_dj*AAt[kk]
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kPipeQ; ++q) {
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) acc[c] += tp[q * cap + 32 * c];      // temp[row] += lij_dj*AAt[kk]
+                    }
                 }
+                g += pair ? 2 : 1;
                 __syncwarp();
-                if (lane == 0) vbk_st_volatile(&cons[0], g + 1);
+                if (lane == 0) vbk_sts_release(&cons[0], g);
                 VBK_PTICK(1);
             }
         } else if (warp == 1) {
@@ -365,12 +379,6 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                 //     its own rows remain to be staged.
                 const bool isfull = valid && cnt > 0 && len == cnt;
                 const bool ispart = valid && len > 0 && !isfull;
-                if (!a.two_pass && valid && !flag) {
-                    while (vbk_ld_volatile(&a.col_done[j]) == 0) { __nanosleep(20); vbk_pause(); }
-                    (void)vbk_ld_acquire(&a.col_done[j]);
-                    lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]);
-                    flag = 1;
-                }
                 const unsigned readym = __ballot_sync(0xffffffffu, !valid || flag != 0);
                 const unsigned fullm = __ballot_sync(0xffffffffu, isfull);
                 const unsigned partm = __ballot_sync(0xffffffffu, ispart);
@@ -403,9 +411,8 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                     if (nflag) { nlij = __ldcg(&a.L[nk]); ndj = __ldcg(&a.diag[nj]); }
                 }
                 // (7) publish the stage
-                __threadfence_block();
                 __syncwarp();
-                if (lane == 0) vbk_st_volatile(&full[st], g + 1);
+                if (lane == 0) vbk_sts_release(&full[st], g + 1);
                 VBK_PTICK(7);
                 if (PROF && profiling) pacc[PROF ? 14 : 0] += 1;
                 k = nk; j = nj; kb = nkb; len = nlen; valid = nvalid; flag = nflag; lij = nlij; dj = ndj;

@@ -20,7 +20,7 @@ import harness as H  # noqa: E402
 spec = importlib.util.spec_from_file_location("vbkkt", "linear-programming-vanderbei_b200/__init__.py")
 vb = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(vb)
-lib = vb.load()
+lib = vb.load(os.environ.get("VBK_LIB"))
 
 
 def run(name, reps, tag):

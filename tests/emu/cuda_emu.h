@@ -28,6 +28,7 @@
 #define __global__
 #define __device__
 #define __host__
+#define __noinline__ __attribute__((noinline))
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
@@ -138,6 +139,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     return v;
 }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
