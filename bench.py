@@ -607,10 +607,10 @@ def main():
         with torch.cuda.stream(stream):
             fy.copy_(ry_d); fx.copy_(rx_d); gy.copy_(b_d); gx.copy_(c_d)
         K.factor_dev(E_d.data_ptr(), D_d.data_ptr())
-        K.solve_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr())
-        p1 = K.last_passes
-        K.solve_dev(E_d.data_ptr(), D_d.data_ptr(), gy.data_ptr(), gx.data_ptr())
-        passes_seen.append(p1 + K.last_passes)
+        # both systems of the iteration (hsd.c:223,228) through the two-right-hand-side sweeps, as the product's own
+        # METHOD plugin runs them; the e2e arm below makes the reference's two separate forwardbackward calls
+        K.solve2_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr(), gy.data_ptr(), gx.data_ptr())
+        passes_seen.append(K.last_passes2(0) + K.last_passes2(1))
 
     for _ in range(a.warmup):
         step_dev()
@@ -770,8 +770,7 @@ def main():
                 with torch.cuda.stream(s2):
                     fy.copy_(ry_d); fx.copy_(rx_d); gy.copy_(b_d); gx.copy_(c_d)
                 K2.factor_dev(E_d.data_ptr(), D_d.data_ptr())
-                K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr())
-                K2.solve_dev(E_d.data_ptr(), D_d.data_ptr(), gy.data_ptr(), gx.data_ptr())
+                K2.solve2_dev(E_d.data_ptr(), D_d.data_ptr(), fy.data_ptr(), fx.data_ptr(), gy.data_ptr(), gx.data_ptr())
             torch.cuda.synchronize()
             for _ in range(3):
                 step2()

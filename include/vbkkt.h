@@ -88,9 +88,16 @@ void vbk_kkt_analyze(vbk_kkt *h, int m, int n, const int *kA, const int *iA, con
                      const int *kAt, const int *iAt, const double *At);
 void vbk_kkt_factor(vbk_kkt *h, const double *dn, const double *dm);
 int  vbk_kkt_solve(vbk_kkt *h, const double *Dn, const double *Dm, double *dx, double *dy);
+/* The two systems of one hsd iteration (reference src/ipo/hsd.c:223 and :228: two forwardbackward calls on the same
+ * factor with independent right-hand sides) in one pair of sweeps per refinement pass.  Each right-hand side gets the
+ * reference's own arithmetic and refinement rule (ldlt.c:367-416): the results equal two vbk_kkt_solve calls bit for bit.
+ * Returns consistent0 | consistent1 << 1; vbk_kkt_last_passes2 gives the refinement passes of each. */
+int  vbk_kkt_solve2(vbk_kkt *h, const double *Dn, const double *Dm, double *dx0, double *dy0, double *dx1, double *dy1);
 /* device-pointer variants (no host traffic); all on the handle's stream, asynchronous */
 void vbk_kkt_factor_dev(vbk_kkt *h, const double *dn_dev, const double *dm_dev);
 int  vbk_kkt_solve_dev(vbk_kkt *h, const double *Dn_dev, const double *Dm_dev, double *dx_dev, double *dy_dev);
+int  vbk_kkt_solve2_dev(vbk_kkt *h, const double *Dn_dev, const double *Dm_dev, double *dx0_dev, double *dy0_dev,
+                        double *dx1_dev, double *dy1_dev);
 /* one raw forward/diagonal/backward sweep (ldlt.c:433-505) on a permuted host vector of length m+n */
 int  vbk_kkt_rawsolve(vbk_kkt *h, double *zperm);
 void vbk_kkt_sync(vbk_kkt *h);
@@ -116,6 +123,7 @@ void   vbk_kkt_get_factor(vbk_kkt *h, double *L, double *diag, int *mark);
 double vbk_kkt_epsdiag(vbk_kkt *h);
 int    vbk_kkt_ndep(vbk_kkt *h);
 int    vbk_kkt_last_passes(const vbk_kkt *h);
+int    vbk_kkt_last_passes2(const vbk_kkt *h, int rhs);    /* after vbk_kkt_solve2: rhs = 0 or 1 */
 long long vbk_kkt_launches(const vbk_kkt *h);
 
 /* profile of the last vbk_solver_* / vbk_solve_lp call (seconds; GPU work bracketed by stream syncs) */

@@ -90,6 +90,12 @@ def _declare(lib):
     lib.vbk_kkt_factor_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vbk_kkt_solve_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vbk_kkt_solve_dev.restype = C.c_int
+    lib.vbk_kkt_solve2_dev.argtypes = [C.c_void_p] * 7
+    lib.vbk_kkt_solve2_dev.restype = C.c_int
+    lib.vbk_kkt_solve2.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.vbk_kkt_solve2.restype = C.c_int
+    lib.vbk_kkt_last_passes2.argtypes = [C.c_void_p, C.c_int]
+    lib.vbk_kkt_last_passes2.restype = C.c_int
     lib.vbk_kkt_rawsolve.argtypes = [C.c_void_p, _dp]
     lib.vbk_kkt_rawsolve.restype = C.c_int
     lib.vbk_kkt_sync.argtypes = [C.c_void_p]
@@ -263,6 +269,14 @@ class KKT:
         ok = self.lib.vbk_kkt_solve(self.h, _d(Dn), _d(Dm), _d(dx), _d(dy))
         return dx, dy, int(ok)
 
+    def solve2(self, Dn, Dm, dx0, dy0, dx1, dy1):
+        """Two right-hand sides on the same factor (the two forwardbackward calls of an hsd iteration, hsd.c:223,228)
+        in one pair of sweeps per refinement pass.  Returns ((dx0, dy0, consistent0), (dx1, dy1, consistent1))."""
+        Dn, Dm = _ad(Dn), _ad(Dm)
+        dx0, dy0, dx1, dy1 = (_ad(v).copy() for v in (dx0, dy0, dx1, dy1))
+        ok = int(self.lib.vbk_kkt_solve2(self.h, _d(Dn), _d(Dm), _d(dx0), _d(dy0), _d(dx1), _d(dy1)))
+        return (dx0, dy0, ok & 1), (dx1, dy1, (ok >> 1) & 1)
+
     def rawsolve(self, zperm):
         z = _ad(zperm).copy()
         self.lib.vbk_kkt_rawsolve(self.h, _d(z))
@@ -290,6 +304,13 @@ class KKT:
 
     def solve_dev(self, Dn_ptr, Dm_ptr, dx_ptr, dy_ptr):
         return int(self.lib.vbk_kkt_solve_dev(self.h, Dn_ptr, Dm_ptr, dx_ptr, dy_ptr))
+
+    def solve2_dev(self, Dn_ptr, Dm_ptr, dx0_ptr, dy0_ptr, dx1_ptr, dy1_ptr):
+        """both systems of an hsd iteration (hsd.c:223,228) in one pair of sweeps per refinement pass"""
+        return int(self.lib.vbk_kkt_solve2_dev(self.h, Dn_ptr, Dm_ptr, dx0_ptr, dy0_ptr, dx1_ptr, dy1_ptr))
+
+    def last_passes2(self, rhs):
+        return int(self.lib.vbk_kkt_last_passes2(self.h, rhs))
 
     def sync(self):
         self.lib.vbk_kkt_sync(self.h)

@@ -206,6 +206,16 @@ int vbk_kkt_solve(vbk_kkt* h, const double* Dn, const double* Dm, double* dx, do
 {
     return h->impl.solve_host(Dn, Dm, dx, dy);
 }
+int vbk_kkt_solve2(vbk_kkt* h, const double* Dn, const double* Dm, double* dx0, double* dy0, double* dx1, double* dy1)
+{
+    return h->impl.solve2_host(Dn, Dm, dx0, dy0, dx1, dy1);
+}
+int vbk_kkt_solve2_dev(vbk_kkt* h, const double* Dn, const double* Dm, double* dx0, double* dy0, double* dx1, double* dy1)
+{
+    int cons[2] = {1, 1};
+    h->impl.solve2_dev(Dn, Dm, dx0, dy0, dx1, dy1, cons);
+    return cons[0] | (cons[1] << 1);
+}
 void vbk_kkt_factor_dev(vbk_kkt* h, const double* dn, const double* dm) { h->impl.factor_dev(dn, dm); }
 int vbk_kkt_solve_dev(vbk_kkt* h, const double* Dn, const double* Dm, double* dx, double* dy)
 {
@@ -240,6 +250,7 @@ void vbk_kkt_get_factor(vbk_kkt* h, double* L, double* diag, int* mark) { h->imp
 double vbk_kkt_epsdiag(vbk_kkt* h) { return h->impl.epsdiag(); }
 int vbk_kkt_ndep(vbk_kkt* h) { return h->impl.ndep(); }
 int vbk_kkt_last_passes(const vbk_kkt* h) { return h->impl.stats.last_passes; }
+int vbk_kkt_last_passes2(const vbk_kkt* h, int rhs) { return h->impl.stats.last_passes2[rhs ? 1 : 0]; }
 long long vbk_kkt_launches(const vbk_kkt* h) { return h->impl.stats.kernel_launches; }
 
 }  // extern "C"

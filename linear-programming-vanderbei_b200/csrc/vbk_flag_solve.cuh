@@ -26,6 +26,8 @@ struct FlagSolveArgs {
     int* done; int* counters;
     const unsigned long long* scal_bits;
     double epssol;
+    double* z2 = nullptr;   // second right-hand side (k_fwd_flags<2>): same structure, same waits, its own chain
+    int rhs = 0;            // scalar slots of z when there is one right-hand side
 };
 
 static __global__ void k_flags_reset(int N, int* __restrict__ done, int* __restrict__ counters, int set_consistent)
@@ -33,7 +35,7 @@ static __global__ void k_flags_reset(int N, int* __restrict__ done, int* __restr
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) done[t] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         counters[C_NEXT] = 0;
-        if (set_consistent) counters[C_CONSISTENT] = 1;
+        if (set_consistent) { counters[C_CONSISTENT] = 1; counters[C_CONSISTENT2] = 1; }
     }
 }
 
@@ -53,22 +55,28 @@ __device__ __forceinline__ double chain_sub(double acc, const double* p, int cnt
     return acc;
 }
 
-__device__ __forceinline__ double flag_solve_eps(const FlagSolveArgs& a) {
-    return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;   // ldlt.c:446
+__device__ __forceinline__ double flag_solve_eps(const FlagSolveArgs& a, int rhs = 0) {
+    return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX + kRhsSlotStride * rhs]) : 0.0;   // ldlt.c:446
 }
 
+// NRHS = 2: two right-hand sides in one sweep (solve2: the two systems of an hsd iteration share the factor).  The
+// sweep is bound by its dependency chain, not by arithmetic: lane 0 runs the chain of z, lane 1 the chain of z2, side by
+// side in the same instructions, and every wait, row list and L value is shared.
+template <int NRHS>
 static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArgs a)
 {
     VBK_DYN_SMEM(raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sp = reinterpret_cast<double*>(raw) + warp * 32;                    // products
-    const double eps = flag_solve_eps(a);
+    double* sp = reinterpret_cast<double*>(raw) + warp * 32 * NRHS;             // products: [NRHS][32]
+    const int myrhs = (NRHS == 2) ? (lane & 1) : a.rhs;                          // slots of the chain this lane may run
+    const double eps = flag_solve_eps(a, myrhs);
+    double* const zmine = (NRHS == 2 && lane == 1) ? a.z2 : a.z;
     for (;;) {
         int r = 0;
         if (lane == 0) r = atomicAdd(&a.counters[C_NEXT], 1);
         r = __shfl_sync(0xffffffffu, r, 0);
         if (r >= a.nclaim) break;
-        double acc = a.z[r];                         // right-hand side entry, written before the launch
+        double acc = zmine[r];                       // right-hand side entry, written before the launch
         const int rb = a.rowptr[r], re = a.rowptr[r + 1];
         // the row's entries 32 at a time; the static part of the NEXT batch (column, L value) is fetched while this one
         // waits for its columns and runs its chain
@@ -92,17 +100,20 @@ static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArg
             }
             // z[j] is read only after its flag has been seen set (control dependency) and bypasses L1; the writer
             // released z before raising the flag
-            double p = 0.0;        // an unmarked column contributes nothing (ldlt.c:455); x - (+0.0) == x
-            if (j >= 0 && a.mark[j]) p = l * __ldcg(&a.z[j]);
-            sp[lane] = p;
+            const bool live = j >= 0 && a.mark[j];   // an unmarked column contributes nothing (ldlt.c:455); x - (+0.0) == x
+            sp[lane] = live ? l * __ldcg(&a.z[j]) : 0.0;
+            if (NRHS == 2) sp[32 + lane] = live ? l * __ldcg(&a.z2[j]) : 0.0;
             __syncwarp();
-            if (lane == 0) acc = chain_sub(acc, sp, (re - t0 < 32) ? (re - t0) : 32);   // z[row] -= AAt[k]*beta
+            if (lane < NRHS) acc = chain_sub(acc, sp + 32 * lane, (re - t0 < 32) ? (re - t0) : 32);   // z[row] -= AAt[k]*beta
             __syncwarp();
         }
+        if (lane < NRHS) {
+            if (a.mark[r]) zmine[r] = acc;
+            else if (fabs(acc) > eps) { zmine[r] = acc; a.counters[C_CONSISTENT + myrhs] = 0; }
+            else zmine[r] = 0.0;
+        }
+        if (NRHS == 2) __syncwarp();
         if (lane == 0) {
-            if (a.mark[r]) a.z[r] = acc;
-            else if (fabs(acc) > eps) { a.z[r] = acc; a.counters[C_CONSISTENT] = 0; }
-            else a.z[r] = 0.0;
             vbk_fence_release();
             atomicExch(&a.done[r], 1);
         }

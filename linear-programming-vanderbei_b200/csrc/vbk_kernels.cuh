@@ -38,12 +38,15 @@ enum ScalarSlot {
     S_ZMAX,          // bits of maxv(z, m) for rawsolve's eps (ldlt.c:446)
     S_MAXBC_B, S_MAXBC_C,   // bits of maxv(b), maxv(c) (ldlt.c:367)
     S_MAXR, S_MAXS,  // bits of maxv(r), maxv(s) (ldlt.c:401)
+    S_ZMAX2, S_MAXBC_B2, S_MAXBC_C2, S_MAXR2, S_MAXS2,   // the same five for the second right-hand side of solve2
     S_COUNT
 };
+constexpr int kRhsSlotStride = 5;     // S_ZMAX + kRhsSlotStride * rhs etc.: scalar slots of right-hand side `rhs` (0 or 1)
 enum CounterSlot {
     C_NEXT = 0,      // column claim counter of the running dataflow kernel
     C_NDEP,          // dependent pivots of the last factorisation (ldlt.c:558,604)
     C_CONSISTENT,    // rawsolve's consistency flag (ldlt.c:439)
+    C_CONSISTENT2,   // ... of the second right-hand side of solve2
     C_COUNT
 };
 
@@ -141,11 +144,12 @@ struct SolveArgs {
     int* counters;
     const unsigned long long* scal_bits;
     double epssol;
+    int rhs = 0;       // which right-hand side's scalar slots (solve2)
 };
 
 __device__ __forceinline__ double solve_eps(const SolveArgs& a) {
     // ldlt.c:446: if (ndep) eps = epssol * maxv(z,m)
-    return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;
+    return a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX + kRhsSlotStride * a.rhs]) : 0.0;
 }
 
 static __global__ void k_diag_strict(SolveArgs a)
@@ -154,7 +158,7 @@ static __global__ void k_diag_strict(SolveArgs a)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += gridDim.x * blockDim.x) {
         double v = a.z[i];
         if (a.mark[i]) a.z[i] = v / a.diag[i];                  // ldlt.c:476
-        else if (fabs(v) > eps) a.counters[C_CONSISTENT] = 0;
+        else if (fabs(v) > eps) a.counters[C_CONSISTENT + a.rhs] = 0;
         else a.z[i] = 0.0;
     }
 }

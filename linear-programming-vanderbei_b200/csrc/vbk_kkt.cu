@@ -4,6 +4,7 @@
 #include "vbk_strict_factor.cuh"
 #include "vbk_strict_solve.cuh"
 
+#include <stdexcept>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -315,49 +316,74 @@ void Kkt::factor_dev(const double* d_dn, const double* d_dm)
     stats.kernel_launches += 9;
 }
 
-void Kkt::rawsolve_dev()
+void Kkt::rawsolve_dev() { rawsolve_rhs(1); }
+
+// mask 1: z_ (right-hand side 0); 2: z2_ (right-hand side 1 on its own); 3: both in one pair of sweeps
+void Kkt::rawsolve_rhs(int mask)
 {
     require_device("rawsolve");
     const int N = sym_.N;
-    stats.rawsolve_calls++;
+    stats.rawsolve_calls += (mask == 3) ? 2 : 1;
+    if (mask != 1 && !z2_.p) throw std::runtime_error("vbkkt: rawsolve on the second right-hand side before solve2");
+    double* const zsingle = (mask == 2) ? z2_.p : z_.p;
+    const int rhs_single = (mask == 2) ? 1 : 0;
     SolveArgs sa;
     sa.N = N; sa.m_ld = sym_.m;
     sa.kL = kL_.p; sa.iL = iL_.p; sa.L = L_.p; sa.diag = diag_.p; sa.mark = mark_.p;
     sa.rowptr = rowptr_.p; sa.rk = rk_asc_.p; sa.rj = rj_asc_.p;
-    sa.parent = parent_.p; sa.z = z_.p; sa.counters = counters_.p;
+    sa.parent = parent_.p; sa.z = zsingle; sa.counters = counters_.p;
     sa.scal_bits = bits_.p; sa.epssol = 1.0e-6;            // _EPSSOL, ldlt.c:28
+    sa.rhs = rhs_single;
 
     // eps = epssol*maxv(z,m) is only used when the factorisation met dependent pivots (ldlt.c:446)
-    VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_ZMAX, 1);
-    VBK_LAUNCH(k_absmax, vec_grid(sym_.m), kVecThreads, 0, stream_, sym_.m, z_.p, bits_.p + S_ZMAX);
+    for (int r = 0; r < 2; ++r) {
+        if (!(mask & (1 << r))) continue;
+        VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_ZMAX + kRhsSlotStride * r, 1);
+        VBK_LAUNCH(k_absmax, vec_grid(sym_.m), kVecThreads, 0, stream_, sym_.m, r ? z2_.p : z_.p, bits_.p + S_ZMAX + kRhsSlotStride * r);
+    }
     FlagSolveArgs fs;
     fs.N = N; fs.kL = kL_.p; fs.iL = iL_.p; fs.L = L_.p; fs.diag = diag_.p; fs.mark = mark_.p;
     fs.rowptr = rowptr_.p; fs.rk = rk_asc_.p; fs.rj = rj_asc_.p; fs.parent = parent_.p;
-    fs.z = z_.p; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
+    fs.z = zsingle; fs.done = done_.p; fs.counters = counters_.p; fs.scal_bits = bits_.p; fs.epssol = 1.0e-6;
     fs.nclaim = N;
     fs.fast = 0;
+    fs.rhs = rhs_single;
+    if (mask == 3) { fs.z = z_.p; fs.z2 = z2_.p; }
     const size_t sm = (size_t)(kSolveThreads / 32) * 128 * sizeof(double);
     if (mode_ == kFast && sym_.dense_start < N && fast_ready_) {
+        if (mask != 1) throw std::runtime_error("vbkkt: the fast-mode window sweeps take one right-hand side");
         rawsolve_window_fast(fs, sa, sm);     // flag kernels below the window, dense sweeps on it
         return;
     }
     // forward: per-column completion flags (vbk_flag_solve.cuh); backward: producer/consumer pipeline per column
+    // (resets both consistency flags: the one of a right-hand side that is not in this call was read by the host already)
     VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
-    VBK_LAUNCH(k_fwd_flags, solve_grid_, kSolveThreads, sm, stream_, fs);
-    VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
+    if (mask == 3) VBK_LAUNCH(k_fwd_flags<2>, solve_grid_, kSolveThreads, sm, stream_, fs);
+    else           VBK_LAUNCH(k_fwd_flags<1>, solve_grid_, kSolveThreads, sm, stream_, fs);
+    if (mask == 3) {
+        SolveArgs sb = sa;
+        sa.z = z_.p; sa.rhs = 0;
+        sb.z = z2_.p; sb.rhs = 1;
+        VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
+        VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sb);
+    } else {
+        VBK_LAUNCH(k_diag_strict, vec_grid(N), kVecThreads, 0, stream_, sa);
+    }
     VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 0);
     {
         BwdPipeArgs ba;
-        ba.N = N; ba.nclaim = N; ba.kL = kL_.p; ba.iL = iL_.p; ba.L = L_.p; ba.mark = mark_.p; ba.z = z_.p;
+        ba.N = N; ba.nclaim = N; ba.kL = kL_.p; ba.iL = iL_.p; ba.L = L_.p; ba.mark = mark_.p; ba.z = fs.z;
+        ba.z2 = fs.z2; ba.rhs = rhs_single;
         ba.done = done_.p; ba.counters = counters_.p; ba.scal_bits = bits_.p; ba.epssol = 1.0e-6;
         int g = (int)std::max<long long>(1, std::min<long long>((long long)num_sms_ * 6, N));
 #ifdef VBK_EMU
         g = std::min(g, 3);
 #endif
-        VBK_LAUNCH(k_bwd_pipe, g, kBwdWarps * 32, bwd_pipe_smem_bytes(), stream_, ba);
+        if (mask == 3) VBK_LAUNCH(k_bwd_pipe<2>, g, kBwdWarps * 32, bwd_pipe_smem_bytes(2), stream_, ba);
+        else           VBK_LAUNCH(k_bwd_pipe<1>, g, kBwdWarps * 32, bwd_pipe_smem_bytes(1), stream_, ba);
     }
     VBK_CHECK_LAUNCH();
-    stats.kernel_launches += 7;
+    stats.kernel_launches += (mask == 3) ? 10 : 7;
 }
 
 void Kkt::spmv_A(const double* d_x, double* d_y)
@@ -375,59 +401,115 @@ void Kkt::spmv_At(const double* d_x, double* d_y)
 
 int Kkt::solve_dev(const double* d_Dn, const double* d_Dm, double* d_c, double* d_b)
 {
+    double* c[2] = {d_c, nullptr};
+    double* b[2] = {d_b, nullptr};
+    int cons[2] = {1, 1};
+    solve_rhs(1, d_Dn, d_Dm, c, b, cons);
+    return cons[0];
+}
+
+// The two systems of one hsd iteration (hsd.c:223 and :228) share the factor and do not depend on each other: both
+// right-hand sides go through ONE pair of sweeps per refinement pass (the sweeps are bound by their dependency chain,
+// so the second right-hand side is almost free).  Each right-hand side keeps the reference's own refinement state
+// (ldlt.c:367-416) and arithmetic; when only one of them needs another pass it runs alone.
+void Kkt::solve2_dev(const double* d_Dn, const double* d_Dm, double* d_c0, double* d_b0, double* d_c1, double* d_b1,
+                     int consistent[2])
+{
+    double* c[2] = {d_c0, d_c1};
+    double* b[2] = {d_b0, d_b1};
+    if (mode_ == kFast && sym_.dense_start < sym_.N && fast_ready_) {     // fast-mode window sweeps: one at a time
+        consistent[0] = solve_dev(d_Dn, d_Dm, d_c0, d_b0);
+        const int p0 = stats.last_passes;
+        consistent[1] = solve_dev(d_Dn, d_Dm, d_c1, d_b1);
+        stats.last_passes2[0] = p0; stats.last_passes2[1] = stats.last_passes;
+        return;
+    }
+    solve_rhs(3, d_Dn, d_Dm, c, b, consistent);
+}
+
+void Kkt::solve_rhs(int mask, const double* d_Dn, const double* d_Dm, double* const d_c[2], double* const d_b[2], int consistent[2])
+{
     require_device("solve");
     VBK_CUDA(cudaSetDevice(device_));
     const int n = sym_.n, m = sym_.m, N = sym_.N;
-    stats.solve_calls++;
-
-    VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_MAXBC_B, 2);
-    VBK_LAUNCH(k_absmax, vec_grid(m), kVecThreads, 0, stream_, m, d_b, bits_.p + S_MAXBC_B);
-    VBK_LAUNCH(k_absmax, vec_grid(n), kVecThreads, 0, stream_, n, d_c, bits_.p + S_MAXBC_C);
-    stats.kernel_launches += 3;
-
-    int pass = 0, consistent = 1;
-    double maxrs = HUGE_VAL, oldmaxrs = HUGE_VAL, maxbc = 1.0;
-    do {
-        if (pass == 0) VBK_LAUNCH(k_permute_in, vec_grid(N), kVecThreads, 0, stream_, n, m, iperm_.p, d_c, d_b, z_.p);
-        else           VBK_LAUNCH(k_permute_in, vec_grid(N), kVecThreads, 0, stream_, n, m, iperm_.p, s_.p, r_.p, z_.p);
-        rawsolve_dev();
-        VBK_LAUNCH(k_permute_out, vec_grid(N), kVecThreads, 0, stream_, n, m, pass == 0 ? 0 : 1, iperm_.p, z_.p, xk_.p, yk_.p);
-        VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_MAXR, 2);
-        // r = b - (A x_k + Dm y_k) ; s = c - (At y_k - Dn x_k)      (ldlt.c:389-398)
-        VBK_LAUNCH(k_residual, vec_grid(m), kVecThreads, 0, stream_, m, 1, gA_ptr_.p, gA_idx_.p, gA_val_.p,
-                   xk_.p, d_Dm, yk_.p, d_b, r_.p, bits_.p + S_MAXR);
-        VBK_LAUNCH(k_residual, vec_grid(n), kVecThreads, 0, stream_, n, 0, gAt_ptr_.p, gAt_idx_.p, gAt_val_.p,
-                   yk_.p, d_Dn, xk_.p, d_c, s_.p, bits_.p + S_MAXS);
-        stats.kernel_launches += 5;
-        read_scalars();
-        consistent = pin_cnt_[C_CONSISTENT];
-        if (pass == 0) {
-            double mb, mc;
-            std::memcpy(&mb, &pin_bits_[S_MAXBC_B], 8);
-            std::memcpy(&mc, &pin_bits_[S_MAXBC_C], 8);
-            maxbc = (mb > mc ? mb : mc) + 1;                                   // ldlt.c:367
-        }
-        double mr, ms;
-        std::memcpy(&mr, &pin_bits_[S_MAXR], 8);
-        std::memcpy(&ms, &pin_bits_[S_MAXS], 8);
-        oldmaxrs = maxrs;
-        maxrs = (mr > ms ? mr : ms);                                            // ldlt.c:401
-        pass++;
-        if (debug_) std::fprintf(stderr, "vbk solve: pass %d maxr %.17g maxs %.17g maxbc %.17g consistent %d\n",
-                                 pass, mr, ms, maxbc, consistent);
-    } while (maxrs > 1.0e-10 * maxbc && maxrs < oldmaxrs / 2);                  // ldlt.c:411
-
-    if (maxrs > oldmaxrs && pass > 1) {                                         // ldlt.c:413-416
-        VBK_LAUNCH(k_permute_out, vec_grid(N), kVecThreads, 0, stream_, n, m, 2, iperm_.p, z_.p, xk_.p, yk_.p);
-        stats.kernel_launches++;
+    if (mask & 2) {
+        if (!z2_.p) { z2_.alloc(N); xk2_.alloc(n); yk2_.alloc(m); r2_.alloc(m); s2_.alloc(n); }
     }
-    VBK_CUDA(cudaMemcpyAsync(d_c, xk_.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, stream_));
-    VBK_CUDA(cudaMemcpyAsync(d_b, yk_.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, stream_));
+    double* const zz[2] = {z_.p, z2_.p};
+    double* const xk[2] = {xk_.p, xk2_.p};
+    double* const yk[2] = {yk_.p, yk2_.p};
+    double* const rr[2] = {r_.p, r2_.p};
+    double* const ss[2] = {s_.p, s2_.p};
+    int pass[2] = {0, 0};
+    double maxrs[2] = {HUGE_VAL, HUGE_VAL}, oldmaxrs[2] = {HUGE_VAL, HUGE_VAL}, maxbc[2] = {1.0, 1.0};
+    int active = mask;
+
+    for (int q = 0; q < 2; ++q) {
+        if (!(mask & (1 << q))) continue;
+        stats.solve_calls++;
+        const int o = kRhsSlotStride * q;
+        VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_MAXBC_B + o, 2);
+        VBK_LAUNCH(k_absmax, vec_grid(m), kVecThreads, 0, stream_, m, d_b[q], bits_.p + S_MAXBC_B + o);
+        VBK_LAUNCH(k_absmax, vec_grid(n), kVecThreads, 0, stream_, n, d_c[q], bits_.p + S_MAXBC_C + o);
+        stats.kernel_launches += 3;
+    }
+    while (active) {
+        for (int q = 0; q < 2; ++q) {
+            if (!(active & (1 << q))) continue;
+            if (pass[q] == 0) VBK_LAUNCH(k_permute_in, vec_grid(N), kVecThreads, 0, stream_, n, m, iperm_.p, d_c[q], d_b[q], zz[q]);
+            else              VBK_LAUNCH(k_permute_in, vec_grid(N), kVecThreads, 0, stream_, n, m, iperm_.p, ss[q], rr[q], zz[q]);
+        }
+        rawsolve_rhs(active);
+        for (int q = 0; q < 2; ++q) {
+            if (!(active & (1 << q))) continue;
+            const int o = kRhsSlotStride * q;
+            VBK_LAUNCH(k_permute_out, vec_grid(N), kVecThreads, 0, stream_, n, m, pass[q] == 0 ? 0 : 1, iperm_.p, zz[q], xk[q], yk[q]);
+            VBK_LAUNCH(k_zero_bits, 1, 32, 0, stream_, bits_.p, (int)S_MAXR + o, 2);
+            // r = b - (A x_k + Dm y_k) ; s = c - (At y_k - Dn x_k)      (ldlt.c:389-398)
+            VBK_LAUNCH(k_residual, vec_grid(m), kVecThreads, 0, stream_, m, 1, gA_ptr_.p, gA_idx_.p, gA_val_.p,
+                       xk[q], d_Dm, yk[q], d_b[q], rr[q], bits_.p + S_MAXR + o);
+            VBK_LAUNCH(k_residual, vec_grid(n), kVecThreads, 0, stream_, n, 0, gAt_ptr_.p, gAt_idx_.p, gAt_val_.p,
+                       yk[q], d_Dn, xk[q], d_c[q], ss[q], bits_.p + S_MAXS + o);
+            stats.kernel_launches += 5;
+        }
+        read_scalars();
+        int next = 0;
+        for (int q = 0; q < 2; ++q) {
+            if (!(active & (1 << q))) continue;
+            const int o = kRhsSlotStride * q;
+            consistent[q] = pin_cnt_[C_CONSISTENT + q];
+            if (pass[q] == 0) {
+                double mb, mc;
+                std::memcpy(&mb, &pin_bits_[S_MAXBC_B + o], 8);
+                std::memcpy(&mc, &pin_bits_[S_MAXBC_C + o], 8);
+                maxbc[q] = (mb > mc ? mb : mc) + 1;                                // ldlt.c:367
+            }
+            double mr, ms;
+            std::memcpy(&mr, &pin_bits_[S_MAXR + o], 8);
+            std::memcpy(&ms, &pin_bits_[S_MAXS + o], 8);
+            oldmaxrs[q] = maxrs[q];
+            maxrs[q] = (mr > ms ? mr : ms);                                         // ldlt.c:401
+            pass[q]++;
+            if (debug_) std::fprintf(stderr, "vbk solve: rhs %d pass %d maxr %.17g maxs %.17g maxbc %.17g consistent %d\n",
+                                     q, pass[q], mr, ms, maxbc[q], consistent[q]);
+            if (maxrs[q] > 1.0e-10 * maxbc[q] && maxrs[q] < oldmaxrs[q] / 2) next |= 1 << q;   // ldlt.c:411
+        }
+        active = next;
+    }
+    for (int q = 0; q < 2; ++q) {
+        if (!(mask & (1 << q))) continue;
+        if (maxrs[q] > oldmaxrs[q] && pass[q] > 1) {                                // ldlt.c:413-416
+            VBK_LAUNCH(k_permute_out, vec_grid(N), kVecThreads, 0, stream_, n, m, 2, iperm_.p, zz[q], xk[q], yk[q]);
+            stats.kernel_launches++;
+        }
+        VBK_CUDA(cudaMemcpyAsync(d_c[q], xk[q], sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, stream_));
+        VBK_CUDA(cudaMemcpyAsync(d_b[q], yk[q], sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, stream_));
+        stats.last_passes2[q] = pass[q];
+    }
     VBK_CHECK_LAUNCH();
-    stats.last_passes = pass;
-    stats.last_consistent = consistent;
+    stats.last_passes = (mask & 1) ? pass[0] : pass[1];
+    stats.last_consistent = (mask & 1) ? consistent[0] : consistent[1];
     stats.last_ndep = pin_cnt_[C_NDEP];
-    return consistent;
 }
 
 void Kkt::factor_host(const double* dn, const double* dm)
@@ -453,6 +535,27 @@ int Kkt::solve_host(const double* Dn, const double* Dm, double* c, double* b)
     h_b_.download(b, sym_.m, stream_);
     VBK_CUDA(cudaStreamSynchronize(stream_));
     return consistent;
+}
+
+int Kkt::solve2_host(const double* Dn, const double* Dm, double* c0, double* b0, double* c1, double* b1)
+{
+    require_device("solve2");
+    VBK_CUDA(cudaSetDevice(device_));
+    if (!h_c2_.p) { h_c2_.alloc(sym_.n); h_b2_.alloc(sym_.m); }
+    h_dn_.upload(Dn, sym_.n, stream_);
+    h_dm_.upload(Dm, sym_.m, stream_);
+    h_c_.upload(c0, sym_.n, stream_);
+    h_b_.upload(b0, sym_.m, stream_);
+    h_c2_.upload(c1, sym_.n, stream_);
+    h_b2_.upload(b1, sym_.m, stream_);
+    int cons[2] = {1, 1};
+    solve2_dev(h_dn_.p, h_dm_.p, h_c_.p, h_b_.p, h_c2_.p, h_b2_.p, cons);
+    h_c_.download(c0, sym_.n, stream_);
+    h_b_.download(b0, sym_.m, stream_);
+    h_c2_.download(c1, sym_.n, stream_);
+    h_b2_.download(b1, sym_.m, stream_);
+    VBK_CUDA(cudaStreamSynchronize(stream_));
+    return cons[0] | (cons[1] << 1);
 }
 
 }  // namespace vbk

@@ -46,6 +46,7 @@ struct KktStats {
     long long factor_calls = 0, solve_calls = 0, rawsolve_calls = 0;
     long long kernel_launches = 0;
     int last_passes = 0, last_consistent = 1, last_ndep = 0;
+    int last_passes2[2] = {0, 0};     // refinement passes of the two right-hand sides of the last solve2
 };
 
 class Kkt {
@@ -65,8 +66,13 @@ public:
     // K^{-1} rhs with iterative refinement; c (length n) and b (length m) are overwritten
     // (solve, ldlt.c:327-425).  Returns the `consistent` flag.
     int solve_dev(const double* d_Dn, const double* d_Dm, double* d_c, double* d_b);
+    // two independent right-hand sides on the same factor in one pair of sweeps per refinement pass (hsd.c:223,228)
+    void solve2_dev(const double* d_Dn, const double* d_Dm, double* d_c0, double* d_b0, double* d_c1, double* d_b1, int consistent[2]);
+    int solve2_host(const double* Dn, const double* Dm, double* c0, double* b0, double* c1, double* b1);
     // one forward/diagonal/backward sweep on the permuted vector in zbuf() (rawsolve, ldlt.c:433-505)
     void rawsolve_dev();
+    void rawsolve_rhs(int mask);
+    void solve_rhs(int mask, const double* d_Dn, const double* d_Dm, double* const d_c[2], double* const d_b[2], int consistent[2]);
 
     // host-pointer wrappers (the B1 seam): H2D, device work, D2H
     void factor_host(const double* dn, const double* dm);
@@ -124,6 +130,8 @@ private:
     DevArray<unsigned long long> bits_;
     // solve work vectors
     DevArray<double> z_, xk_, yk_, r_, s_;
+    DevArray<double> z2_, xk2_, yk2_, r2_, s2_;       // second right-hand side (solve2), allocated on first use
+    DevArray<double> h_c2_, h_b2_;
     // host-seam staging
     DevArray<double> h_dn_, h_dm_, h_c_, h_b_;
     // pinned readback

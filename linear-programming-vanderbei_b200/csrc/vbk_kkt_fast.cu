@@ -304,7 +304,7 @@ void Kkt::rawsolve_window_fast(FlagSolveArgs& fs, SolveArgs& sa, size_t flag_sme
     const int ggather = std::max(1, std::min(num_sms_ * 4, (W * 32 + kSolveThreads - 1) / kSolveThreads));
 
     VBK_LAUNCH(k_flags_reset, vec_grid(N), kVecThreads, 0, stream_, N, done_.p, counters_.p, 1);
-    if (T > 0) VBK_LAUNCH(k_fwd_flags, gsolve, kSolveThreads, flag_smem, stream_, fs);
+    if (T > 0) VBK_LAUNCH(k_fwd_flags<1>, gsolve, kSolveThreads, flag_smem, stream_, fs);
     VBK_LAUNCH(k_window_gather, ggather, kSolveThreads, 0, stream_, wa);
     // window: 128-row panels with inverted diagonal blocks (vbk_window_solve.cuh)
     Tri3Args t3;

@@ -268,22 +268,19 @@ static int solver_hsd_impl(bool longstep, int device, int mode, int m, int n, in
         }
         VBK_LAUNCH(k_neg_copy, W.g(n), kVecThreads, 0, st, n, W.sigma.p, fx.p);
         VBK_LAUNCH(k_copy, W.g(m), kVecThreads, 0, st, m, W.rho.p, fy.p);
-        W.launches(2);
-        capture_in(iter, st, m, n, W.E.p, W.D.p, fy.p, fx.p);
-        {
-            Timer t(timed, st, timed ? &prof->solve_s : nullptr);
-            W.kkt.solve_dev(W.E.p, W.D.p, fy.p, fx.p);                          // hsd.c:223
-        }
-        capture_out(iter, st, m, n, fy.p, fx.p);
-        if (timed) prof->refine_passes += W.kkt.stats.last_passes;
         VBK_LAUNCH(k_neg_copy, W.g(n), kVecThreads, 0, st, n, W.c.p, gx.p);
         VBK_LAUNCH(k_neg_copy, W.g(m), kVecThreads, 0, st, m, W.b.p, gy.p);
-        W.launches(2);
+        W.launches(4);
+        capture_in(iter, st, m, n, W.E.p, W.D.p, fy.p, fx.p);
         {
+            // the two systems of the iteration (hsd.c:223 and :228) have independent right-hand sides: one pair of
+            // sweeps per refinement pass serves both
             Timer t(timed, st, timed ? &prof->solve_s : nullptr);
-            W.kkt.solve_dev(W.E.p, W.D.p, gy.p, gx.p);                          // hsd.c:228
+            int cons2[2];
+            W.kkt.solve2_dev(W.E.p, W.D.p, fy.p, fx.p, gy.p, gx.p, cons2);
         }
-        if (timed) prof->refine_passes += W.kkt.stats.last_passes;
+        capture_out(iter, st, m, n, fy.p, fx.p);
+        if (timed) prof->refine_passes += W.kkt.stats.last_passes2[0] + W.kkt.stats.last_passes2[1];
 
         {
             DotJob jobs[4] = {{W.c.p, fx.p, n}, {W.b.p, fy.p, m}, {W.c.p, gx.p, n}, {W.b.p, gy.p, m}};

@@ -35,20 +35,28 @@ struct BwdPipeArgs {
     double* z;
     int* done;         // [N] 1 once z[i] is final (zeroed before the launch; columns >= nclaim count as final)
     int* counters; const unsigned long long* scal_bits; double epssol;
+    double* z2 = nullptr;   // second right-hand side (k_bwd_pipe<2>)
+    int rhs = 0;            // scalar slots of z when there is one right-hand side
 };
 
-inline size_t bwd_pipe_smem_bytes() { return sizeof(double) * kBwdStages * kBwdChunk + sizeof(int) * (kBwdStages + 4); }
+inline size_t bwd_pipe_smem_bytes(int nrhs = 1) { return sizeof(double) * nrhs * kBwdStages * kBwdChunk + sizeof(int) * (kBwdStages + 4); }
 
+// NRHS = 2: the even lanes of the consumer warp run the chain of z, the odd lanes the chain of z2 (same instructions,
+// two shared-memory addresses per load); the producers stage both products of an entry behind one wait.
+template <int NRHS>
 static __global__ void __launch_bounds__(kBwdWarps * 32) k_bwd_pipe(BwdPipeArgs a)
 {
     VBK_DYN_SMEM(raw);
-    double* ring = reinterpret_cast<double*>(raw);              // [kBwdStages][kBwdChunk]
-    int* full = reinterpret_cast<int*>(ring + kBwdStages * kBwdChunk);   // [kBwdStages] chunk number + 1
+    double* ring = reinterpret_cast<double*>(raw);              // [NRHS][kBwdStages][kBwdChunk]
+    int* full = reinterpret_cast<int*>(ring + NRHS * kBwdStages * kBwdChunk);   // [kBwdStages] chunk number + 1
     int* cons = full + kBwdStages;                              // [0] chunks consumed
     int* s_ctl = cons + 1;                                      // [0] claim
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int P = kBwdWarps - 1;
-    const double eps = a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX]) : 0.0;   // ldlt.c:446
+    const int myrhs = (NRHS == 2) ? (lane & 1) : a.rhs;
+    const double eps = a.counters[C_NDEP] ? a.epssol * bits_to_double(a.scal_bits[S_ZMAX + kRhsSlotStride * myrhs]) : 0.0;   // ldlt.c:446
+    double* const zmine = (NRHS == 2 && (lane & 1)) ? a.z2 : a.z;
+    const double* const myring = ring + ((NRHS == 2 && (lane & 1)) ? kBwdStages * kBwdChunk : 0);
 
     for (;;) {
         __syncthreads();
@@ -64,23 +72,24 @@ static __global__ void __launch_bounds__(kBwdWarps * 32) k_bwd_pipe(BwdPipeArgs 
         const int nchunks = marked ? (ke - kb + kBwdChunk - 1) / kBwdChunk : 0;
 
         if (warp == 0) {
-            double beta = a.z[i];                       // z[i] after the diagonal sweep (previous launch)
+            double beta = zmine[i];                     // z[i] after the diagonal sweep (previous launch)
             if (marked) {
                 for (int g = 0; g < nchunks; ++g) {
                     const int st = g % kBwdStages;
                     while (vbk_lds_acquire(&full[st]) != g + 1) vbk_pause();
-                    const double* p = ring + st * kBwdChunk;
+                    const double* p = myring + st * kBwdChunk;
                     // fully unrolled: the compiler keeps a few loads ahead of the dependent subtractions
 #pragma unroll
                     for (int q = 0; q < kBwdChunk; ++q) beta = beta - p[q];         // z[i] -= AAt[k]*z[row], ldlt.c:494
                     __syncwarp();
                     if (lane == 0) vbk_sts_release(&cons[0], g + 1);
                 }
-                if (lane == 0) a.z[i] = beta;
-            } else if (lane == 0) {
-                if (fabs(beta) > eps) a.counters[C_CONSISTENT] = 0;
-                else a.z[i] = 0.0;
+                if (lane < NRHS) zmine[i] = beta;
+            } else if (lane < NRHS) {
+                if (fabs(beta) > eps) a.counters[C_CONSISTENT + myrhs] = 0;
+                else zmine[i] = 0.0;
             }
+            if (NRHS == 2) __syncwarp();
             if (lane == 0) { vbk_fence_release(); atomicExch(&a.done[i], 1); }
         } else {
             const int pw = warp - 1;
@@ -105,13 +114,19 @@ static __global__ void __launch_bounds__(kBwdWarps * 32) k_bwd_pipe(BwdPipeArgs 
                 }
                 // The z loads below are issued only after the polls have returned (control dependency) and bypass L1, the
                 // writer released z before raising the flag: the classic volatile-flag hand-off, no reader-side fence.
-                double zr[4];
+                double zr[4], zr2[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) zr[u] = (r[u] >= 0) ? __ldcg(&a.z[r[u]]) : 0.0;
+                for (int u = 0; u < 4; ++u) {
+                    zr[u] = (r[u] >= 0) ? __ldcg(&a.z[r[u]]) : 0.0;
+                    zr2[u] = (NRHS == 2 && r[u] >= 0) ? __ldcg(&a.z2[r[u]]) : 0.0;
+                }
                 if (g >= kBwdStages) { while (vbk_lds_acquire(&cons[0]) < g - kBwdStages + 1) vbk_pause(); }
                 double* p = ring + st * kBwdChunk + lane;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) p[32 * u] = l[u] * zr[u];       // +0.0 beyond the column's end: x - (+0.0) == x
+                for (int u = 0; u < 4; ++u) {
+                    p[32 * u] = l[u] * zr[u];           // +0.0 beyond the column's end: x - (+0.0) == x
+                    if (NRHS == 2) p[kBwdStages * kBwdChunk + 32 * u] = l[u] * zr2[u];
+                }
                 __syncwarp();
                 if (lane == 0) vbk_sts_release(&full[st], g + 1);
             }

@@ -59,12 +59,27 @@ def check_kkt_step(vbkkt, lib, oracle, lp, method, it, refine_rhs=True):
         assert np.array_equal(d, F.diag)
         assert np.array_equal(L, F.L)
         assert K.ndep == F.ndep
+        ndep1 = F.ndep
         oy, ox, _ = F.solve(E, D, ry, rx)
         gy, gx, _ = K.solve(E, D, ry, rx)
+        oy_passes = F.passes
         assert K.last_passes == F.passes
         assert np.array_equal(gy, oy) and np.array_equal(gx, ox)
         z = np.random.default_rng(it).standard_normal(lp.m + lp.n)
         assert np.array_equal(K.rawsolve(z), F.rawsolve(z))
+        # both systems of an hsd iteration (hsd.c:223,228) in one pair of sweeps: each right-hand side must come out
+        # exactly as from its own forwardbackward call, with its own number of refinement passes -- in either slot
+        rng = np.random.default_rng(1000 + it)
+        qy, qx = -lp.b * (1 + 1e-3 * rng.standard_normal(lp.m)), -lp.c * (1 + 1e-3 * rng.standard_normal(lp.n))
+        o2y, o2x, _ = F.solve(E, D, qy, qx)
+        p2 = F.passes
+        for (a, b) in (((ry, rx), (qy, qx)), ((qy, qx), (ry, rx))):
+            r0, r1 = K.solve2(E, D, a[0], a[1], b[0], b[1])
+            want0, want1 = ((oy, ox), (o2y, o2x)) if a[0] is ry else ((o2y, o2x), (oy, ox))
+            assert np.array_equal(r0[0], want0[0]) and np.array_equal(r0[1], want0[1])
+            assert np.array_equal(r1[0], want1[0]) and np.array_equal(r1[1], want1[1])
+            passes = (K.last_passes2(0), K.last_passes2(1))
+            assert passes == ((oy_passes, p2) if a[0] is ry else (p2, oy_passes))
         # a second factorisation on the same handles: state carried across calls (epsdiag
         # escalation ldlt.c:293-306, mark reset ldlt.c:280) must stay in lock step
         F.factor(E * 0.5, D * 2.0)
@@ -72,7 +87,7 @@ def check_kkt_step(vbkkt, lib, oracle, lp, method, it, refine_rhs=True):
         L, d, mk = K.get_factor()
         assert np.array_equal(mk, F.mark) and np.array_equal(d, F.diag) and np.array_equal(L, F.L)
         assert K.epsdiag == float(oracle.kko_epsdiag(F.h))
-        return dict(ndep=F.ndep, passes=F.passes, lnz=K.lnz)
+        return dict(ndep=ndep1, passes=oy_passes, lnz=K.lnz)
     finally:
         F.close()
         K.close()
