@@ -61,6 +61,9 @@ def mcf_workload(name):
     """Synthetic multicommodity LP + a synthetic mid-solve iterate (E, D log-uniform over six decades like the x/z,
     y/w ratios of an interior-point iterate; right-hand sides standard normal).  No reference solution is stored:
     the bench checks the KKT residual of the GPU solution instead (size-independent property)."""
+    # orderings of these LPs computed once on the host (tests/golden/make_symcache.py, 8 bytes per row/column): the
+    # library reads them instead of repeating minutes of explicit-fill minimum degree (SURVEY H6)
+    os.environ.setdefault("VBK_SYM_CACHE", str(ROOT / "tests" / "golden" / "symcache"))
     vbw = _load("vbkkt_workloads", ROOT / "linear-programming-vanderbei_b200" / "workloads.py")
     parts = name.split(":")
     R, K = (int(parts[1]), int(parts[2])) if len(parts) == 3 else (32, 25)

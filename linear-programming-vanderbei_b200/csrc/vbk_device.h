@@ -77,6 +77,15 @@ __device__ __forceinline__ void vbk_pause() {      // spin-loop body: yields the
     sched_yield();
 #endif
 }
+// spin-loop body of a warp that is NOT on the critical path: sleeps, so that its polling does not take issue slots
+// from the warp of the same scheduler that runs a dependent chain
+__device__ __forceinline__ void vbk_backoff(unsigned ns) {
+#ifdef VBK_EMU
+    (void)ns; sched_yield();
+#else
+    __nanosleep(ns);
+#endif
+}
 __device__ __forceinline__ void vbk_st_volatile(int* p, int v) {
 #ifdef VBK_EMU
     __atomic_store_n(p, v, __ATOMIC_RELEASE);

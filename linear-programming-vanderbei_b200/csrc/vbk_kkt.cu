@@ -219,6 +219,7 @@ void Kkt::launch_factor_pipe(int ntasks, bool timed)
     pa.winptr = winptr_.p; pa.nblk = sym_.nblk; pa.rowblk = sym_.rowblk; pa.slice_row0 = sym_.slice_row0;
     pa.col_pub = col_pub_.p; pa.col_done = col_done_.p; pa.task_max = task_max_.p;
     pa.counters = counters_.p; pa.scal_bits = bits_.p; pa.epsnum = 0.0;        // _EPSNUM, ldlt.c:29
+    { const char* e = std::getenv("VBK_PIPE_BACKOFF"); pa.backoff_ns = e ? (unsigned)std::atoi(e) : 256u; }
     if (std::getenv("VBK_PROF") && !prof_.p) { prof_.alloc(16); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 128, stream_)); }
     pa.prof = prof_.p;
     if (pa.prof && !trace_.p) trace_.alloc((size_t)N * 8);

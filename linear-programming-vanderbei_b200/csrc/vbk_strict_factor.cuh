@@ -58,6 +58,7 @@ struct PipeArgs {
     int* col_done;      // [N] 1 once L[:,j], diag[j] and mark[j] are final
     double* task_max;   // [ntasks] max|undivided entry| of a non-owner slice
     int* counters; const unsigned long long* scal_bits; double epsnum;
+    unsigned backoff_ns;    // sleep of a producer between two looks at a full ring
     // optional [16] cycle counters ($VBK_PROF), lane 0 of each role: 0 consumer waits for a stage, 1 consumer adds,
     // 2 producer waits for a free slot, 3 static structure + zero fill, 4 waits for the contributors' columns,
     // 5 fence + lij, dj, 6 products, 7 publish; 8 claim + task setup, 9 epilogue up to col_pub / pivot wait,
@@ -362,7 +363,7 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                 // (2) a free ring slot
                 if (g >= S) {
                     const int need = g - S + 1;
-                    while (vbk_ld_volatile(&cons[0]) < need || (owner && vbk_ld_volatile(&cons[1]) < need)) vbk_pause();
+                    while (vbk_ld_volatile(&cons[0]) < need || (owner && vbk_ld_volatile(&cons[1]) < need)) vbk_backoff(a.backoff_ns);
                     __threadfence_block();
                 }
                 VBK_PTICK(2);

@@ -11,6 +11,7 @@
 namespace vbk {
 
 namespace {
+constexpr long long kSymCacheMagic = 0x324d59534b4256ll;   // "VBKSYM2": ordering only
 
 // Indexed binary min-heap, positions 1..count.  Tie behaviour must equal the reference's static
 // hfall/hrise pair (ldlt.c:1305-1349): the right child wins only when strictly smaller, and an
@@ -219,6 +220,37 @@ void Symbolic::order(std::vector<std::vector<int>>& adj, std::vector<int>& tier)
     narth = narth + 3.0 * kL[N] + N;
 }
 
+// Fill pattern of L from the ordering alone (used when the ordering comes from the disk cache): column j of L holds the
+// rows > j of K's permuted column j merged with the patterns of j's elimination-tree children -- the classic symbolic
+// factorisation, O(Lnz).  The reference's explicit-fill elimination (ldlt.c:1050-1236) produces exactly this set, rows
+// ascending (checked against it on the netlib fixtures, tests/test_host.py).
+void Symbolic::pattern_from_ordering(const std::vector<std::vector<int>>& adj, size_t lnz_hint) {
+    std::vector<std::vector<int>> kids(N);
+    std::vector<int> mark(N, -1);
+    kL.assign((size_t)N + 1, 0);
+    iL.clear();
+    iL.reserve(lnz_hint);
+    for (int j = 0; j < N; ++j) {
+        const size_t b0 = iL.size();
+        mark[j] = j;
+        for (int u : adj[perm[j]]) {
+            const int r = iperm[u];
+            if (r > j && mark[r] != j) { mark[r] = j; iL.push_back(r); }
+        }
+        for (int k : kids[j]) {
+            for (int q = kL[k]; q < kL[k + 1]; ++q) {
+                const int r = iL[q];
+                if (mark[r] != j) { mark[r] = j; iL.push_back(r); }
+            }
+        }
+        std::vector<int>().swap(kids[j]);
+        std::sort(iL.begin() + b0, iL.end());
+        if (iL.size() > 0x7fffffffu) { std::fprintf(stderr, "vbkkt: L has more than 2^31-1 entries (32-bit ABI, SURVEY H5)\n"); std::exit(1); }
+        kL[j + 1] = (int)iL.size();
+        if (iL.size() > b0) kids[iL[b0]].push_back(j);
+    }
+}
+
 void Symbolic::analyze(int m_, int n_, const int* kA, const int* iA, const int* kAt, const int* iAt) {
     m = m_; n = n_; N = m + n; nzA = kA[n];
 
@@ -255,8 +287,8 @@ void Symbolic::analyze(int m_, int n_, const int* kA, const int* iA, const int* 
     dense = 3;  // ldlt.c:814-846 with n1 == 0
 
     const auto t0 = std::chrono::steady_clock::now();
-    // $VBK_SYM_CACHE=<directory>: the ordering and the fill pattern (perm, iperm, kAAt, iAAt, denwin, narth) are kept on
-    // disk, keyed by a hash of the matrix pattern (the explicit-fill ordering of the largest synthetic LPs
+    // $VBK_SYM_CACHE=<directory>: the ordering (perm, iperm, denwin, narth: 8 bytes per row/column of K) is kept on disk,
+    // keyed by a hash of the matrix pattern; the fill pattern is rebuilt from it by an elimination-tree pass in O(Lnz) (the explicit-fill ordering of the largest synthetic LPs
     // takes minutes to an hour, for the reference as for any faithful restatement, and depends on the pattern only)
     std::string cache_file;
     if (const char* dir = std::getenv("VBK_SYM_CACHE")) {
@@ -275,13 +307,14 @@ void Symbolic::analyze(int m_, int n_, const int* kA, const int* iA, const int* 
         if (FILE* f = std::fopen(cache_file.c_str(), "rb")) {
             long long hd[8] = {0};
             double na = 0;
-            if (std::fread(hd, sizeof hd, 1, f) == 1 && std::fread(&na, sizeof na, 1, f) == 1 && hd[0] == 0x314d59534b4256ll &&
+            if (std::fread(hd, sizeof hd, 1, f) == 1 && std::fread(&na, sizeof na, 1, f) == 1 && hd[0] == kSymCacheMagic &&
                 hd[1] == m && hd[2] == n && hd[3] == nzA && hd[4] == N) {
-                const size_t lnz_ = (size_t)hd[5];
-                perm.resize(N); iperm.resize(N); kL.resize((size_t)N + 1); iL.resize(lnz_);
-                cached = std::fread(perm.data(), sizeof(int), N, f) == (size_t)N && std::fread(iperm.data(), sizeof(int), N, f) == (size_t)N &&
-                         std::fread(kL.data(), sizeof(int), (size_t)N + 1, f) == (size_t)N + 1 &&
-                         std::fread(iL.data(), sizeof(int), lnz_, f) == lnz_ && kL[N] == (int)lnz_;
+                perm.resize(N); iperm.resize(N);
+                cached = std::fread(perm.data(), sizeof(int), N, f) == (size_t)N && std::fread(iperm.data(), sizeof(int), N, f) == (size_t)N;
+                if (cached) {
+                    pattern_from_ordering(adj, (size_t)hd[5]);          // the fill pattern is a function of the ordering
+                    cached = (long long)kL[N] == hd[5];
+                }
                 denwin = (int)hd[6]; narth = na;
                 if (!cached) std::fprintf(stderr, "vbkkt: symbolic cache %s is damaged; recomputing\n", cache_file.c_str());
             }
@@ -293,11 +326,9 @@ void Symbolic::analyze(int m_, int n_, const int* kA, const int* iA, const int* 
         if (!cache_file.empty()) {
             const std::string tmp = cache_file + ".tmp";
             if (FILE* f = std::fopen(tmp.c_str(), "wb")) {
-                const long long hd[8] = {0x314d59534b4256ll, m, n, nzA, N, (long long)kL[N], denwin, pdf};
+                const long long hd[8] = {kSymCacheMagic, m, n, nzA, N, (long long)kL[N], denwin, pdf};
                 bool ok = std::fwrite(hd, sizeof hd, 1, f) == 1 && std::fwrite(&narth, sizeof narth, 1, f) == 1 &&
-                          std::fwrite(perm.data(), sizeof(int), N, f) == (size_t)N && std::fwrite(iperm.data(), sizeof(int), N, f) == (size_t)N &&
-                          std::fwrite(kL.data(), sizeof(int), (size_t)N + 1, f) == (size_t)N + 1 &&
-                          std::fwrite(iL.data(), sizeof(int), (size_t)kL[N], f) == (size_t)kL[N];
+                          std::fwrite(perm.data(), sizeof(int), N, f) == (size_t)N && std::fwrite(iperm.data(), sizeof(int), N, f) == (size_t)N;
                 ok = (std::fclose(f) == 0) && ok;
                 if (ok) std::rename(tmp.c_str(), cache_file.c_str()); else std::remove(tmp.c_str());
             }

@@ -67,6 +67,7 @@ struct Symbolic {
 
 private:
     void order(std::vector<std::vector<int>>& adj, std::vector<int>& tier);
+    void pattern_from_ordering(const std::vector<std::vector<int>>& adj, size_t lnz_hint);
     void derive(const int* kA, const int* iA, const int* kAt, const int* iAt);
 };
 

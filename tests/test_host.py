@@ -98,19 +98,26 @@ def test_multicommodity_bench_workload(vbkkt, product_lib):
 
 
 def test_symbolic_disk_cache_round_trip(vbkkt, emu_lib, tmp_path, monkeypatch):
-    """$VBK_SYM_CACHE: the second analysis of a pattern reads perm / kAAt / iAAt back from disk and yields the same
-    arrays; a different pattern gets its own file."""
+    """$VBK_SYM_CACHE: the second analysis of a pattern reads the ORDERING back from disk, rebuilds the fill pattern from
+    it (elimination-tree pass) and yields the same arrays as the full analysis -- which in turn equal the
+    compiled reference's (fixture); a different pattern gets its own file.  Problems with and without a dense window."""
     monkeypatch.setenv("VBK_SYM_CACHE", str(tmp_path))
-    outs = []
-    for name in ("afiro", "afiro", "sc50b"):
+    names = ("afiro", "sc50b", "israel", "25fv47", "ken-07", "pilotnov")
+    for name in names:
         lp = H.load_fixture(name)
         kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
-        K = vbkkt.KKT(device=-1, lib=emu_lib)
-        K.analyze(lp.n, lp.m, kAt, iAt, At, lp.kA, lp.iA, lp.A)
-        outs.append((K.perm, K.iperm, K.kAAt, K.iAAt, K.denwin, K.narth))
-        K.close()
-    assert len(list(tmp_path.glob("vbksym_*.bin"))) == 2
-    for a, b in zip(outs[0], outs[1]):
-        assert np.array_equal(a, b)
-    lp = H.load_fixture("afiro")
-    assert np.array_equal(outs[1][0], lp.extra["sym_perm"]) and np.array_equal(outs[1][2], lp.extra["sym_kAAt"])
+        outs = []
+        for _ in range(2):
+            K = vbkkt.KKT(device=-1, lib=emu_lib)
+            K.analyze(lp.n, lp.m, kAt, iAt, At, lp.kA, lp.iA, lp.A)
+            outs.append((K.perm, K.iperm, K.kAAt, K.iAAt, K.denwin, K.narth))
+            K.close()
+        for a, b in zip(outs[0], outs[1]):
+            assert np.array_equal(a, b), name
+        assert np.array_equal(outs[1][0], lp.extra["sym_perm"]) and np.array_equal(outs[1][2], lp.extra["sym_kAAt"])
+        assert np.array_equal(outs[1][3], lp.extra["sym_iAAt"])
+    files = list(tmp_path.glob("vbksym_*.bin"))
+    assert len(files) == len(names)
+    sizes = sorted(f.stat().st_size for f in files)
+    want = sorted(72 + 8 * (H.load_fixture(nm).m + H.load_fixture(nm).n) for nm in names)   # ordering only: 8 bytes per row/column of K
+    assert sizes == want
