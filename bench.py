@@ -852,7 +852,8 @@ def main():
 
         out = {"metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f64", "data": "netlib LP fixture + oracle-generated hsd iterate (tests/golden)",
+               "dtype": "f64", "data": ("synthetic multicommodity LP (generator seed 1) + synthetic iterate (seed 20)" if a.workload.startswith("mcf")
+                                        else "netlib LP fixture + oracle-generated hsd iterate (tests/golden)"),
                "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                "cpu_baseline": cpu, "strict_mode": strict, "fast_mode": fast, "solve_time": solve_time,
                "flops_per_step": flops_step, "rawsolves_per_step": raw_per_step,

@@ -159,6 +159,11 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
         done_.alloc(N); task_max_.alloc(std::max(ntasks, 1));
     }
     // strict factor kernel (vbk_strict_factor.cuh): launch geometry
+    if (!sym_.tasks_ok && mode_ != kFast) {
+        std::fprintf(stderr, "vbkkt: this LP (N = %d) is too large for the strict factor kernel's per-column block table; "
+                             "use fast mode (VBK_MODE=fast)\n", N);
+        std::exit(1);
+    }
     {
         const int ntasks = sym_.ntasks();
         int max_cnt = 1;

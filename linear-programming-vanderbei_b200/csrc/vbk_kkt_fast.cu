@@ -95,7 +95,7 @@ void Kkt::prepare_fast()
 void Kkt::factor_window_fast()
 {
     const int N = sym_.N, T = sym_.dense_start, W = N - T;
-    const int sparse_tasks = sym_.col_task0[T];
+    const int sparse_tasks = sym_.tasks_ok ? sym_.col_task0[T] : 0;
     int launches = 2;
 
     // 1. columns j < T keep the reference's arithmetic.  Two kernels produce the same bits for them -- the strict slice
@@ -111,7 +111,11 @@ void Kkt::factor_window_fast()
     const bool levels_ok = sp_smem <= (size_t)smem_optin_ && sph_smem <= (size_t)smem_optin_;
     bool sparse_levels = levels_ok;
     int tune_slot = -1;
-    if (esp && std::string(esp) == "strict") sparse_levels = false;
+    if (!sym_.tasks_ok) {
+        if (!levels_ok) { std::fprintf(stderr, "vbkkt: neither the slice tasks nor the level kernels fit this LP\n"); std::exit(1); }
+        sparse_levels = true;                 // no slice tasks for this LP (vbk_symbolic.cpp)
+    }
+    else if (esp && std::string(esp) == "strict") sparse_levels = false;
     else if (esp && std::string(esp) == "level") sparse_levels = levels_ok;
     else if (levels_ok && sparse_tasks > 0 && T > 0) {
         if (sparse_tuned_ < 2) { tune_slot = sparse_tuned_; sparse_levels = tune_slot == 1; }

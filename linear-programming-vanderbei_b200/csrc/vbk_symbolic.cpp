@@ -444,13 +444,22 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
         if (kL[j + 1] - kL[j] > whole_cap) { slice_row0 = j; break; }
     if (const char* e = std::getenv("VBK_ROWBLK")) rowblk = std::max(1, std::atoi(e)); else rowblk = 32;   // measured on B200: 32 beats 64 (profiles/)
     nblk = 0;
+    tasks_ok = true;
     winptr.clear();
     if (slice_row0 < N) {
         nblk = (N - slice_row0 + rowblk - 1) / rowblk;
-        while ((long long)N * (nblk + 1) > (1LL << 28)) {   // keep the lookup table below 1 GiB
+        while ((long long)N * (nblk + 1) > (1LL << 28) && rowblk < 128) {   // keep the lookup table below 1 GiB
             rowblk *= 2;
             nblk = (N - slice_row0 + rowblk - 1) / rowblk;
         }
+        if ((long long)N * (nblk + 1) > (1LL << 28)) {
+            // The dense per-column block table does not fit at the kernel's largest row block (128): no slice tasks for
+            // this LP.  Fast mode factorises its sparse columns with the level kernels; strict mode refuses the LP.
+            tasks_ok = false;
+            nblk = 0;
+        }
+    }
+    if (slice_row0 < N && tasks_ok) {
         winptr.assign((size_t)N * (nblk + 1), 0);
         for (int j = 0; j < N; ++j) {
             int* wp = &winptr[(size_t)j * (nblk + 1)];
@@ -465,7 +474,7 @@ void Symbolic::derive(const int* kA, const int* iA, const int* kAt, const int* i
     task_col.clear(); task_blk.clear(); task_pos0.clear(); task_cnt.clear();
     col_task0.assign(N, 0);
     col_ntask.assign(N, 0);
-    for (int j = 0; j < N; ++j) {
+    for (int j = 0; j < N && tasks_ok; ++j) {
         col_task0[j] = (int)task_col.size();
         const int c = kL[j + 1] - kL[j];
         if (c <= whole_cap) {

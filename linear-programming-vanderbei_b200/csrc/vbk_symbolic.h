@@ -50,6 +50,7 @@ struct Symbolic {
     // column finds its entries for a block by lookup, never by search.
     int whole_cap = 512;              // $VBK_WHOLE_CAP overrides (tests force slicing on tiny LPs)
     int slice_row0 = 0, rowblk = 64, nblk = 0;
+    bool tasks_ok = true;             // false: the block table would not fit (huge LPs) -- no slice tasks, fast mode only
     std::vector<int> winptr;          // [N*(nblk+1)], empty when no column is sliced
     std::vector<int> task_col, task_blk, task_pos0, task_cnt;   // blk = -1: whole column
     std::vector<int> col_task0, col_ntask;                      // [N]
