@@ -733,7 +733,7 @@ def main():
         fp64 = {"achieved_tflops": K.narth / fac_s / 1e12, "peak_tflops": fp64_peak,
                 "frac": K.narth / fac_s / 1e12 / max(fp64_peak, 1e-9),
                 "peak_source": "measured here (DFMA yardstick kernel, vbk_measure_fp64_tflops; DMMA measures the same "
-                               "37 TFLOP/s, scratch/ubench.cu); MEASURED_PEAKS.json has no FP64 entry"}
+                               "37 TFLOP/s, profiles/ubench/ubench.cu); MEASURED_PEAKS.json has no FP64 entry"}
         hbm = {"achieved_gbs": b_fac / fac_s / 1e9, "peak_gbs": hbm_peak, "frac": b_fac / fac_s / 1e9 / hbm_peak,
                "peak_source": peak_src}
         # a factorisation is held to the FP64 roofline iff its arithmetic intensity (reference flop count over
@@ -751,11 +751,23 @@ def main():
         chain = {"links": int(K.lnz), "ns_per_link": fac_s * 1e9 / max(K.lnz, 1), "floor_ns_per_link": floor_ns,
                  "frac_of_floor": floor_ns / (fac_s * 1e9 / max(K.lnz, 1)),
                  "note": "strict mode is a chain of ~Lnz dependent rounded additions by construction (SURVEY 8d): this is the bound it is held to"}
+        # DRAM traffic of one launch of the dominant kernel: not measurable here (no profiler inside a timed run); the
+        # committed ncu capture of the same workload and mode is quoted when there is one
+        traffic, traffic_note = None, "no ncu capture of this workload/mode in profiles/r02_traffic.json"
+        try:
+            tj = json.load(open(ROOT / "profiles" / "r02_traffic.json"))
+            ent = tj.get(a.workload, {}).get(a.mode)
+            if ent:
+                traffic = ent["bytes_per_launch"]
+                traffic_note = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one {ent['kernel']} launch ({ent['source']}); "
+                                f"L2 -> SM traffic of the same launch: {ent['l2_to_sm_bytes'] / 1e9:.0f} GB, all L2 hits")
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {"kernel": kname, "bound": "tensor" if fp64_bound else "hbm",
                     "achieved": fp64["achieved_tflops"] if fp64_bound else hbm["achieved_gbs"],
                     "peak": fp64_peak if fp64_bound else hbm_peak, "unit": "TFLOP/s" if fp64_bound else "GB/s",
                     "frac": fp64["frac"] if fp64_bound else hbm["frac"],
-                    "traffic": None, "traffic_note": "not measured by this run; ncu DRAM bytes per factorisation are in profiles/ (r02_summary.md)",
+                    "traffic": traffic, "traffic_note": traffic_note,
                     "algorithmic_bytes": b_fac,
                     "peak_source": fp64["peak_source"] if fp64_bound else peak_src,
                     "flop_per_byte": intensity, "kernel_ms": fac_s * 1e3, "share_of_step": fac_s * 1e3 / ms_per_step,

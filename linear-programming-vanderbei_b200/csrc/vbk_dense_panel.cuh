@@ -210,7 +210,7 @@ __device__ double panel_rare_pivot(const DenseArgs& a, int b0, int nbb, int c, d
 // LDL^T of one 32 x 32 sub-block of k_panel_diag by warp 0, row `lane` in the lane's registers.  kRare = false: no
 // dependent-pivot branch, returns whether some pivot failed the test (the caller then repeats the sub-block with
 // kRare = true); finished columns are parked as a = l*d at park[lane * park_ld + c].
-// (Taking this function out of line -- so that it is compiled like the stand-alone micro-benchmark, scratch/ubench2.cu,
+// (Taking this function out of line -- so that it is compiled like the stand-alone micro-benchmark, profiles/ubench/ubench2.cu,
 // 127 cycles per column -- did not help: 440 cycles per column, the shared-memory arrays become generic pointers.)
 #ifndef VBK_EMU
 // (I + L_bb)^-1 of the finished 32 x 32 sub-block starting at column bs of the panel, for the tensor-path rows kernel:
@@ -270,7 +270,7 @@ bool panel_ldl32(const DenseArgs& a, int b0, int nbb, int lane, double* blk, dou
     // updated a_{.,c+1} (ONE fma per lane), column c+1 is published and its pivot's reciprocal started; the
     // other 30 - c updates of column c then fill that latency.  Dependent chain per column: fma, store,
     // load, reciprocal (one MUFU + five fma, no slow-path call), multiply.
-    // Bookkeeping is kept off that chain in the optimistic pass (kRare = false; scratch/ubench2.cu: 126 cycles per
+    // Bookkeeping is kept off that chain in the optimistic pass (kRare = false; profiles/ubench/ubench2.cu: 126 cycles per
     // column bare, 233 with per-column pivot stores + parked column + broadcast term magnitude): the pivot test is
     // made by the lane that owns the pivot on its own registers and voted on once at the end, pivots and
     // reciprocals stay in the owning lane's registers, and the finished columns -- a_{r,c} is not touched again

@@ -14,7 +14,7 @@ constexpr int kUpT = 128;                      // tile edge
 constexpr size_t kUpdPipeSmem = sizeof(double) * kUpStages * 2 * kUpKC * kUpT;   // 96 KB
 
 // ---------------------------------------------------------------------------------------------------------
-// The same update on the FP64 tensor path: mma.sync.m8n8k4 (DMMA).  Measured on B200 (scratch/ubench.cu,
+// The same update on the FP64 tensor path: mma.sync.m8n8k4 (DMMA).  Measured on B200 (profiles/ubench/ubench.cu,
 // profiles/): DMMA peaks at the same 37 TFLOP/s as DFMA (it is the same pipe -- interleaving both adds nothing),
 // but it reaches that peak with 4 warps per SM and 2 accumulators per warp, where an 8 x 8 DFMA outer product
 // needs 8 warps to reach 33 TFLOP/s and spends every second issue slot on it.  More important here: operands.
