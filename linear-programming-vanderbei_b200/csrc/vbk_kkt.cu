@@ -208,23 +208,60 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
 #endif
         }
     }
+    // presence masks of the (task, contributor) pairs (vbk_strict_factor.cuh: k_pipe_masks), once per analysis
+    if (sym_.tasks_ok && sym_.ntasks() > 0) {
+        const int ntasks = sym_.ntasks();
+        std::vector<long long> pair0((size_t)ntasks);
+        long long pairs = 0;
+        for (int t = 0; t < ntasks; ++t) {
+            const int i = sym_.task_col[t];
+            pair0[t] = pairs;
+            pairs += (long long)((sym_.rowptr[i + 1] - sym_.rowptr[i] + kPipeQ - 1) / kPipeQ) * kPipeQ;
+        }
+        const int nch = pipe_cap_ / 32;
+        task_pair0_.upload(pair0, stream_);
+        pipe_masks_.alloc((size_t)std::max<long long>(pairs, 1) * nch);
+        PipeArgs pa;
+        fill_pipe_args(pa, ntasks);
+        int g = std::max(1, std::min(ntasks, num_sms_ * 8));
+#ifdef VBK_EMU
+        g = std::min(g, 3);
+        const int mthreads = 64;
+#else
+        const int mthreads = 256;
+#endif
+        if (nch == 1) VBK_LAUNCH(k_pipe_masks<1>, g, mthreads, 0, stream_, pa, pipe_masks_.p);
+        else if (nch == 2) VBK_LAUNCH(k_pipe_masks<2>, g, mthreads, 0, stream_, pa, pipe_masks_.p);
+        else VBK_LAUNCH(k_pipe_masks<4>, g, mthreads, 0, stream_, pa, pipe_masks_.p);
+        if (debug_) std::fprintf(stderr, "vbk factor: %lld (task, contributor) pairs, %.1f MB of presence masks\n", pairs, pairs * nch * 4 / 1e6);
+    } else {
+        task_pair0_.alloc(1); pipe_masks_.alloc(1);
+    }
     if (mode_ == kFast) prepare_fast();
     VBK_CUDA(cudaStreamSynchronize(stream_));
 }
 
-void Kkt::launch_factor_pipe(int ntasks, bool timed)
+void Kkt::fill_pipe_args(PipeArgs& pa, int ntasks)
 {
     const int N = sym_.N;
-    PipeArgs pa;
     pa.N = N; pa.n_ld = sym_.n; pa.ntasks = ntasks; pa.nstages = pipe_stages_;
     pa.kL = kL_.p; pa.iL = iL_.p; pa.L = L_.p; pa.diag = diag_.p; pa.mark = mark_.p;
     pa.rowptr = rowptr_.p; pa.rk = rk_sig_.p; pa.rj = rj_sig_.p; pa.perm = perm_.p;
     pa.task_col = task_col_.p; pa.task_blk = task_blk_.p; pa.task_pos0 = task_pos0_.p; pa.task_cnt = task_cnt_.p;
     pa.col_task0 = col_task0_.p; pa.col_ntask = col_ntask_.p;
     pa.winptr = winptr_.p; pa.nblk = sym_.nblk; pa.rowblk = sym_.rowblk; pa.slice_row0 = sym_.slice_row0;
+    pa.masks = pipe_masks_.p; pa.task_pair0 = task_pair0_.p;
     pa.col_pub = col_pub_.p; pa.col_done = col_done_.p; pa.task_max = task_max_.p;
     pa.counters = counters_.p; pa.scal_bits = bits_.p; pa.epsnum = 0.0;        // _EPSNUM, ldlt.c:29
     { const char* e = std::getenv("VBK_PIPE_BACKOFF"); pa.backoff_ns = e ? (unsigned)std::atoi(e) : 256u; }
+    pa.prof = nullptr; pa.trace = nullptr;
+}
+
+void Kkt::launch_factor_pipe(int ntasks, bool timed)
+{
+    const int N = sym_.N;
+    PipeArgs pa;
+    fill_pipe_args(pa, ntasks);
     if (std::getenv("VBK_PROF") && !prof_.p) { prof_.alloc(16); VBK_CUDA(cudaMemsetAsync(prof_.p, 0, 128, stream_)); }
     pa.prof = prof_.p;
     if (pa.prof && !trace_.p) trace_.alloc((size_t)N * 8);

@@ -142,6 +142,9 @@ private:
     // slice tasks of the numeric factorisation (vbk_symbolic.h) and the strict factor kernel's hand-off state
     // (vbk_strict_factor.cuh): producer/consumer pipeline per slice task
     DevArray<int> task_col_, task_blk_, task_pos0_, task_cnt_, col_task0_, col_ntask_, winptr_;
+    DevArray<unsigned> pipe_masks_;            // presence masks of the (task, contributor) pairs (k_pipe_masks)
+    DevArray<long long> task_pair0_;           // [ntasks] first pair of a task
+    void fill_pipe_args(struct PipeArgs& pa, int ntasks);
     DevArray<int> col_pub_, col_done_, done_;
     DevArray<double> task_max_;
     DevArray<long long> trace_;            // $VBK_PROF: per-column event times of the strict factor kernel

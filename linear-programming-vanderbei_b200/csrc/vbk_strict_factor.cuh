@@ -54,6 +54,9 @@ struct PipeArgs {
     const int* task_col; const int* task_blk; const int* task_pos0; const int* task_cnt;
     const int* col_task0; const int* col_ntask;
     const int* winptr; int nblk, rowblk, slice_row0;
+    // presence masks (k_pipe_masks, once per analysis): for pair number task_pair0[t] + 32*g + q -- contributor q of group g
+    // of task t -- NCH words whose bit s says that the contributor's column holds row s of the task
+    const unsigned* masks; const long long* task_pair0;
     int* col_pub;       // [N] non-owner slices of the column that have published their undivided entries
     int* col_done;      // [N] 1 once L[:,j], diag[j] and mark[j] are final
     double* task_max;   // [ntasks] max|undivided entry| of a non-owner slice
@@ -100,105 +103,138 @@ static __global__ void k_pipe_reset(int N, int* __restrict__ col_pub, int* __res
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[C_NEXT] = 0; counters[C_NDEP] = 0; }
 }
 
-// Products of (a subset of) one ring stage.  A producer warp is bound by its own instruction stream and by the round
-// trips it exposes, so: few instructions per row, many loads in flight, no shared-memory load behind a store.
-//  * lane q of the warp holds contributor q's record (w = lij*dj, kb = first entry of column j in the rows of the task,
-//    len = how many); rows get it by warp shuffle.
-//  * "full" rows -- the contributor holds every row of the task, the rule in the dense tail -- need neither row indices
-//    nor a zero fill (slot = position): all full rows of the stage are loaded in ONE batch (one exposed round trip).
-//  * the other rows are zero-filled (+0.0 where a contributor has no entry) and scattered through the block's row -> slot
-//    map (BLK) or a branch-free binary search over the task's sorted rows (whole columns), eight rows per batch; all
-//    look-ups of a batch come before its first store.
-// fullm / partm / zerom: one bit per contributor of the stage to handle in this call (warp-uniform).
-template <int NCH, bool BLK>
-__device__ __forceinline__ void pipe_products(const PipeArgs& a, double w, int kb, int len, double* __restrict__ tp,
-                                              unsigned fullm, unsigned partm, unsigned zerom,
-                                              const int* __restrict__ blockmap, const int* __restrict__ rows,
-                                              int cnt, int bs, int lane)
+#ifndef VBK_PIPE_FB
+#define VBK_PIPE_FB 32
+#endif
+
+// Presence masks of every (task, contributor) pair, computed once per analysis: lane = contributor of a group, one
+// CTA-stride loop over the tasks.  Bit s of the pair's mask is set when the contributor's column j holds row s of the
+// task; its entries in the task's rows are consecutive in column j (they start at kb, see the producers), so the entry of
+// slot s is kb + (number of set bits below s).
+template <int NCH>
+static __global__ void k_pipe_masks(PipeArgs a, unsigned* __restrict__ masks)
 {
-    constexpr int cap = 32 * NCH;
-    constexpr int kSteps = (NCH == 1) ? 5 : (NCH == 2 ? 6 : 7);    // log2(cap)
-    const double* Lp = a.L + lane;
-    double* tpl = tp + lane;
-    // full rows, compacted: up to FB of them per batch, all loads of a batch in flight together.  The loads are
-    // UNCONDITIONAL (a predicated load keeps its predicate alive until the value is used, and with seven predicate
-    // registers the compiler then serialises a batch six rows at a time); a slot past the end of the list repeats the
-    // last row (never a fixed dummy address: thousands of warps reading one line make it a hot spot in the L2), lanes
-    // beyond the task's rows read into the next column or the padding behind L.
-    {
-        constexpr int FB = 16 / NCH;
-        unsigned todo = fullm;
-        while (todo) {
-            int qs[FB];
-            double val[FB][NCH];
-            int nrows = 0, qlast = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int wstride = a.nblk + 1;
+    for (int t = blockIdx.x; t < a.ntasks; t += gridDim.x) {
+        const int i = a.task_col[t], blk = a.task_blk[t], p0 = a.task_pos0[t], cnt = a.task_cnt[t];
+        const int rb = a.rowptr[i], re = a.rowptr[i + 1];
+        const int ngroups = (re - rb + kPipeQ - 1) / kPipeQ;
+        const int* trow = a.iL + p0;                  // the task's rows, ascending
+        for (int g = warp; g < ngroups; g += nwarps) {
+            const int tq = rb + g * kPipeQ + lane;
+            unsigned m[NCH];
 #pragma unroll
-            for (int u = 0; u < FB; ++u) {
-                if (todo) { qlast = __ffs(todo) - 1; todo &= todo - 1; ++nrows; }
-                qs[u] = qlast;
-                const int kbq = __shfl_sync(0xffffffffu, kb, qlast);
+            for (int c = 0; c < NCH; ++c) m[c] = 0u;
+            if (tq < re) {
+                const int k = a.rk[tq], j = a.rj[tq];
+                int kb = k + 1, ke = a.kL[j + 1];
+                if (blk >= 0) {
+                    const int* wp = a.winptr + (size_t)j * wstride;
+                    if (wp[blk] > kb) kb = wp[blk];
+                    if (wp[blk + 1] < ke) ke = wp[blk + 1];
+                }
+                int s = 0;                            // both lists ascend: one merge pass
+                for (int e = kb; e < ke; ++e) {
+                    const int r = a.iL[e];
+                    while (s < cnt && trow[s] < r) ++s;
+                    if (s < cnt && trow[s] == r) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) val[u][c] = __ldcg(Lp + kbq + 32 * c);
-            }
-#pragma unroll
-            for (int u = 0; u < FB; ++u) {
-                const double wq = __shfl_sync(0xffffffffu, w, qs[u]);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-                    if (u < nrows && lane + 32 * c < cnt) tpl[qs[u] * cap + 32 * c] = wq * val[u][c];   // lij_dj*AAt[kk], ldlt.c:583
-            }
-        }
-    }
-    if (zerom) {
-#pragma unroll
-        for (int q = 0; q < kPipeQ; ++q) {
-            if ((zerom >> q) & 1u) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) tpl[q * cap + 32 * c] = 0.0;
-            }
-        }
-        __syncwarp();
-    }
-    constexpr int QB = (NCH == 1) ? 8 : (NCH == 2 ? 4 : 2);
-    while (partm) {
-        int qs[QB], lens[QB], ri[QB][NCH], slot[QB][NCH];
-        double wv[QB], val[QB][NCH];
-#pragma unroll
-        for (int u = 0; u < QB; ++u) {
-            qs[u] = partm ? __ffs(partm) - 1 : -1;
-            partm &= partm - 1;
-            const int q = qs[u] < 0 ? 0 : qs[u];
-            const int kbq = __shfl_sync(0xffffffffu, kb, q);
-            const int lq = __shfl_sync(0xffffffffu, len, q);
-            wv[u] = __shfl_sync(0xffffffffu, w, q);
-            lens[u] = qs[u] < 0 ? 0 : lq;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int e = lane + 32 * c;
-                const int idx = kbq + ((e < lens[u]) ? e : 0);        // unconditional loads, see above
-                val[u][c] = __ldcg(a.L + idx);
-                ri[u][c] = a.iL[idx];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < QB; ++u) {
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int e = lane + 32 * c;
-                if (BLK) slot[u][c] = blockmap[(e < lens[u]) ? ri[u][c] - bs : 0];
-                else {
-                    int sl = 0;              // rows[] is sorted and holds the row: largest s with rows[s] <= row
-#pragma unroll
-                    for (int b2 = kSteps - 1; b2 >= 0; --b2) sl += (rows[sl + (1 << b2)] <= ri[u][c]) ? (1 << b2) : 0;
-                    slot[u][c] = sl;
+                        for (int c = 0; c < NCH; ++c) if ((s >> 5) == c) m[c] |= 1u << (s & 31);
+                    }
                 }
             }
+            const size_t pair = (size_t)a.task_pair0[t] + (size_t)g * kPipeQ + lane;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) masks[pair * NCH + c] = m[c];
+        }
+    }
+}
+
+// Products of (a subset of) one ring stage.  A producer warp is bound by its own instruction stream and by the round
+// trips it exposes, so every row is the same few instructions and there are no look-ups at all:
+//  * lane q of the warp holds contributor q's record: w = lij*dj, kb = first entry of column j in the rows of the task,
+//    mask = which of the task's rows column j holds (precomputed, k_pipe_masks); rows get it by warp shuffle;
+//  * lane s of row q loads entry kb + popcount(mask below s) -- its own entry when bit s is set -- and stores
+//    w * value, or +0.0 when the contributor has no entry in that row (x + (+0.0) == x; the accumulator is never -0.0);
+//  * the loads are UNCONDITIONAL (a predicated load keeps its predicate alive until the value is used, and with seven
+//    predicate registers the compiler then serialises a batch six rows at a time) and always hit the contributor's own
+//    entries or the ones right behind them (never a fixed dummy address: thousands of warps reading one line make it a
+//    hot spot in the L2); L is padded for the reads past the last column.
+// rowsel: one bit per contributor of the stage to STORE in this call (warp-uniform); the others are loaded and dropped.
+template <int NCH>
+__device__ __forceinline__ void pipe_products(const PipeArgs& a, double w, int kb, const unsigned (&mask)[NCH], double* __restrict__ tp,
+                                              unsigned rowsel, int cnt, int lane)
+{
+    constexpr int cap = 32 * NCH;
+    constexpr int FB = VBK_PIPE_FB / NCH;          // rows per batch = loads in flight per lane
+    const unsigned lt = (1u << lane) - 1u;
+    double* tpl = tp + lane;
+#pragma unroll 1
+    for (int q0 = 0; q0 < kPipeQ; q0 += FB) {
+        if (((rowsel >> q0) & (FB >= 32 ? 0xffffffffu : ((1u << (FB & 31)) - 1u))) == 0u) continue;      // warp-uniform
+        double val[FB][NCH];
+        unsigned pres[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) pres[c] = 0u;
+#pragma unroll
+        for (int u = 0; u < FB; ++u) {
+            int pos = __shfl_sync(0xffffffffu, kb, q0 + u);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const unsigned m = __shfl_sync(0xffffffffu, mask[c], q0 + u);
+                val[u][c] = __ldcg(a.L + pos + __popc(m & lt));
+                pres[c] |= ((m >> lane) & 1u) << u;
+                if (c + 1 < NCH) pos += __popc(m);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < QB; ++u) {
+        for (int u = 0; u < FB; ++u) {
+            const double wq = __shfl_sync(0xffffffffu, w, q0 + u);
+            const bool sel = (rowsel >> (q0 + u)) & 1u;                 // warp-uniform
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
-                if (lane + 32 * c < lens[u]) tp[qs[u] * cap + slot[u][c]] = wv[u] * val[u][c];        // lij_dj*AAt[kk], ldlt.c:583
+                if (sel && lane + 32 * c < cnt) tpl[(q0 + u) * cap + 32 * c] = ((pres[c] >> u) & 1u) ? wq * val[u][c] : 0.0;   // lij_dj*AAt[kk], ldlt.c:583
+        }
+    }
+}
+
+// The same for a FEW rows (the second pass of a stage: the contributors that were not final when the stage was prepared,
+// as a rule the youngest child alone -- this sits on the critical path between two columns): only the selected rows are
+// loaded, up to four at a time.
+template <int NCH>
+__device__ __forceinline__ void pipe_products_few(const PipeArgs& a, double w, int kb, const unsigned (&mask)[NCH], double* __restrict__ tp,
+                                                  unsigned rowsel, int cnt, int lane)
+{
+    constexpr int cap = 32 * NCH;
+    const unsigned lt = (1u << lane) - 1u;
+    double* tpl = tp + lane;
+    while (rowsel) {
+        int qs[4];
+        double val[4][NCH];
+        unsigned pres[NCH];
+        int nrows = 0, qlast = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) pres[c] = 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (rowsel) { qlast = __ffs(rowsel) - 1; rowsel &= rowsel - 1; ++nrows; }
+            qs[u] = qlast;                             // a slot past the end repeats the last row
+            int pos = __shfl_sync(0xffffffffu, kb, qlast);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const unsigned m = __shfl_sync(0xffffffffu, mask[c], qlast);
+                val[u][c] = __ldcg(a.L + pos + __popc(m & lt));
+                pres[c] |= ((m >> lane) & 1u) << u;
+                if (c + 1 < NCH) pos += __popc(m);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double wq = __shfl_sync(0xffffffffu, w, qs[u]);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                if (u < nrows && lane + 32 * c < cnt) tpl[qs[u] * cap + 32 * c] = ((pres[c] >> u) & 1u) ? wq * val[u][c] : 0.0;   // lij_dj*AAt[kk], ldlt.c:583
         }
     }
 }
@@ -245,13 +281,6 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
         const int rb = a.rowptr[i], re = a.rowptr[i + 1];
         const int ngroups = (re - rb + kPipeQ - 1) / kPipeQ;
 
-        if (blk >= 0) for (int s = tid; s < a.rowblk; s += nt) blockmap[s] = 0;
-        __syncthreads();
-        for (int s = tid; s < cap; s += nt) {
-            int row = 0x7fffffff;
-            if (s < cnt) { row = a.iL[p0 + s]; if (blk >= 0) blockmap[row - bs] = s; }
-            rows[s] = row;
-        }
         if (tid < S) full[tid] = 0;
         if (tid < 2) cons[tid] = 0;
         __syncthreads();
@@ -329,7 +358,11 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
             // while the products of the current one are formed, and so are its readiness flag and lij, dj when the
             // contributing columns are already final -- in steady state only the product loads are exposed.
             const int pw = warp - 2;
-            int k = 0, j = 0, kb = 0, len = 0, flag = 1;
+            const size_t pair0 = (size_t)a.task_pair0[t];
+            int k = 0, j = 0, kb = p0, flag = 1;       // a lane without a contributor reads the task's own entries and stores +0.0
+            unsigned mask[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) mask[c] = 0u;
             bool valid = false;
             double lij = 0.0, dj = 0.0;
             if (pw < ngroups) {
@@ -337,15 +370,10 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                 valid = tq < re;
                 if (valid) {
                     k = a.rk[tq]; j = a.rj[tq];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) mask[c] = a.masks[(pair0 + (size_t)pw * kPipeQ + lane) * NCH + c];
                     kb = k + 1;
-                    int ke = a.kL[j + 1];
-                    if (blk >= 0) {
-                        const int* wp = a.winptr + (size_t)j * wstride;
-                        const int lo = wp[blk], hi = wp[blk + 1];
-                        if (lo > kb) kb = lo;
-                        if (hi < ke) ke = hi;
-                    }
-                    len = ke > kb ? ke - kb : 0;       // entries of column j in the rows of this task
+                    if (blk >= 0) { const int lo = a.winptr[(size_t)j * wstride + blk]; if (lo > kb) kb = lo; }
                     flag = vbk_ld_acquire(&a.col_done[j]);
                     if (flag) { lij = __ldcg(&a.L[k]); dj = __ldcg(&a.diag[j]); }
                 }
@@ -353,12 +381,19 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
             for (int g = pw; g < ngroups; g += P) {
                 const int st = g % S;
                 double* tp = tile + (size_t)st * kPipeQ * cap;
-                // (1) row-list entries of the warp's next group
+                // (1) row-list entries and presence masks of the warp's next group
                 const int gn = g + P;
                 const int tqn = rb + gn * kPipeQ + lane;
                 const bool nvalid = gn < ngroups && tqn < re;
                 int nk = 0, nj = 0;
-                if (nvalid) { nk = a.rk[tqn]; nj = a.rj[tqn]; }
+                unsigned nmask[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) nmask[c] = 0u;
+                if (nvalid) {
+                    nk = a.rk[tqn]; nj = a.rj[tqn];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) nmask[c] = a.masks[(pair0 + (size_t)gn * kPipeQ + lane) * NCH + c];
+                }
                 VBK_PTICK(3);
                 // (2) a free ring slot
                 if (g >= S) {
@@ -367,25 +402,17 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                     __threadfence_block();
                 }
                 VBK_PTICK(2);
-                // (3) column end and block range of the next group's contributors
-                int nke = 0, nlo = 0, nhi = 0x7fffffff;
-                if (nvalid) {
-                    nke = a.kL[nj + 1];
-                    if (blk >= 0) { const int* wp = a.winptr + (size_t)nj * wstride; nlo = wp[blk]; nhi = wp[blk + 1]; }
-                }
+                // (3) first entry of the next group's contributors in the block of this task
+                int nlo = 0;
+                if (nvalid && blk >= 0) nlo = a.winptr[(size_t)nj * wstride + blk];
                 VBK_PTICK(4);
                 // (4) products, in two passes: first every contributor whose column was final when the group was
                 //     prepared -- all of them in steady state, all but the youngest child when the task runs ahead of the
                 //     critical path -- then, as its column becomes final, what is left.  When the last child finishes only
                 //     its own rows remain to be staged.
-                const bool isfull = valid && cnt > 0 && len == cnt;
-                const bool ispart = valid && len > 0 && !isfull;
                 const unsigned readym = __ballot_sync(0xffffffffu, !valid || flag != 0);
-                const unsigned fullm = __ballot_sync(0xffffffffu, isfull);
-                const unsigned partm = __ballot_sync(0xffffffffu, ispart);
                 double w = lij * dj;                                   // lij_dj, ldlt.c:572
-                if (blk >= 0) pipe_products<NCH, true>(a, w, kb, len, tp, fullm & readym, partm & readym, ~fullm, blockmap, rows, cnt, bs, lane);
-                else          pipe_products<NCH, false>(a, w, kb, len, tp, fullm & readym, partm & readym, ~fullm, blockmap, rows, cnt, bs, lane);
+                pipe_products<NCH>(a, w, kb, mask, tp, readym, cnt, lane);
                 VBK_PTICK(5);
                 if (~readym) {
                     if (valid && !flag) {
@@ -395,19 +422,16 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                         w = lij * dj;
                     }
                     __syncwarp();
-                    if (blk >= 0) pipe_products<NCH, true>(a, w, kb, len, tp, fullm & ~readym, partm & ~readym, 0u, blockmap, rows, cnt, bs, lane);
-                    else          pipe_products<NCH, false>(a, w, kb, len, tp, fullm & ~readym, partm & ~readym, 0u, blockmap, rows, cnt, bs, lane);
+                    pipe_products_few<NCH>(a, w, kb, mask, tp, ~readym, cnt, lane);
                 }
                 s_meta[st * kPipeQ + lane].w = w;                      // the pivot chain's operands
                 s_l[st * kPipeQ + lane] = lij;
                 VBK_PTICK(6);
-                // (6) next group: entry range, readiness, lij and dj if the column is final already
-                int nkb = nk + 1, nlen = 0, nflag = 1;
+                // (6) next group: first entry, readiness, lij and dj if the column is final already
+                int nkb = nvalid ? nk + 1 : p0, nflag = 1;
                 double nlij = 0.0, ndj = 0.0;
                 if (nvalid) {
                     if (nlo > nkb) nkb = nlo;
-                    if (nhi < nke) nke = nhi;
-                    nlen = nke > nkb ? nke - nkb : 0;
                     nflag = vbk_ld_acquire(&a.col_done[nj]);
                     if (nflag) { nlij = __ldcg(&a.L[nk]); ndj = __ldcg(&a.diag[nj]); }
                 }
@@ -416,7 +440,9 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                 if (lane == 0) vbk_sts_release(&full[st], g + 1);
                 VBK_PTICK(7);
                 if (PROF && profiling) pacc[PROF ? 14 : 0] += 1;
-                k = nk; j = nj; kb = nkb; len = nlen; valid = nvalid; flag = nflag; lij = nlij; dj = ndj;
+                k = nk; j = nj; kb = nkb; valid = nvalid; flag = nflag; lij = nlij; dj = ndj;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) mask[c] = nmask[c];
             }
         }
 
