@@ -178,8 +178,8 @@ void Kkt::analyze(int m, int n, const int* kA, const int* iA, const double* A,
 #ifndef VBK_EMU
         if (const char* e = std::getenv("VBK_PIPE_WARPS")) pipe_warps_ = std::max(3, std::min(kPipeWarpsDefault, std::atoi(e)));
 #endif
-        pipe_stages_ = kPipeStagesMax;
-        if (const char* e = std::getenv("VBK_PIPE_STAGES")) pipe_stages_ = std::max(2, std::min(16, std::atoi(e)));
+        pipe_stages_ = kPipeStagesMax;        // as many as fit in shared memory (25 for 32-row tasks)
+        if (const char* e = std::getenv("VBK_PIPE_STAGES")) pipe_stages_ = std::max(2, std::min(kPipeStagesMax, std::atoi(e)));
         while (pipe_stages_ > 2 && pipe_smem_bytes(pipe_cap_, pipe_stages_, sym_.rowblk, pipe_warps_) > (size_t)smem_optin_) --pipe_stages_;
         pipe_smem_ = pipe_smem_bytes(pipe_cap_, pipe_stages_, sym_.rowblk, pipe_warps_);
         if (pipe_smem_ > (size_t)smem_optin_) {

@@ -36,13 +36,21 @@
 namespace vbk {
 
 constexpr int kPipeQ = 32;            // contributors per ring stage
+#ifndef VBK_PIPE_MULTI
+#ifdef VBK_EMU
+#define VBK_PIPE_MULTI 2      // the emulated ring has three stages
+#else
+#define VBK_PIPE_MULTI 6
+#endif
+#endif
+constexpr int kPipeMulti = VBK_PIPE_MULTI;      // ring stages a chain takes per flag check (when the ring is deeper than that)
 constexpr int kPipeMaxChains = 4;     // rows per consumer lane: tasks of up to 128 rows
 #ifdef VBK_EMU
 constexpr int kPipeWarpsDefault = 4;  // consumer, pivot, 2 producers (every CUDA thread is an OS thread there)
 constexpr int kPipeStagesMax = 3;
 #else
 constexpr int kPipeWarpsDefault = 16; // consumer, pivot, 14 producers
-constexpr int kPipeStagesMax = 16;
+constexpr int kPipeStagesMax = 32;
 #endif
 
 struct PipeArgs {
@@ -162,40 +170,39 @@ static __global__ void k_pipe_masks(PipeArgs a, unsigned* __restrict__ masks)
 //    entries or the ones right behind them (never a fixed dummy address: thousands of warps reading one line make it a
 //    hot spot in the L2); L is padded for the reads past the last column.
 // rowsel: one bit per contributor of the stage to STORE in this call (warp-uniform); the others are loaded and dropped.
-template <int NCH>
-__device__ __forceinline__ void pipe_products(const PipeArgs& a, double w, int kb, const unsigned (&mask)[NCH], double* __restrict__ tp,
-                                              unsigned rowsel, int cnt, int lane)
+template <int NCH, int FB>
+__device__ __forceinline__ void pipe_load_rows(const PipeArgs& a, int kb, const unsigned (&mask)[NCH], int q0,
+                                               double (&val)[FB][NCH], unsigned (&pres)[NCH], int lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) pres[c] = 0u;
+#pragma unroll
+    for (int u = 0; u < FB; ++u) {
+        int pos = __shfl_sync(0xffffffffu, kb, q0 + u);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const unsigned m = __shfl_sync(0xffffffffu, mask[c], q0 + u);
+            val[u][c] = __ldcg(a.L + pos + __popc(m & lt));
+            pres[c] |= ((m >> lane) & 1u) << u;
+            if (c + 1 < NCH) pos += __popc(m);
+        }
+    }
+}
+
+template <int NCH, int FB>
+__device__ __forceinline__ void pipe_store_rows(double w, int q0, const double (&val)[FB][NCH], const unsigned (&pres)[NCH],
+                                                double* __restrict__ tp, unsigned rowsel, int cnt, int lane)
 {
     constexpr int cap = 32 * NCH;
-    constexpr int FB = VBK_PIPE_FB / NCH;          // rows per batch = loads in flight per lane
-    const unsigned lt = (1u << lane) - 1u;
     double* tpl = tp + lane;
-#pragma unroll 1
-    for (int q0 = 0; q0 < kPipeQ; q0 += FB) {
-        if (((rowsel >> q0) & (FB >= 32 ? 0xffffffffu : ((1u << (FB & 31)) - 1u))) == 0u) continue;      // warp-uniform
-        double val[FB][NCH];
-        unsigned pres[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) pres[c] = 0u;
+    for (int u = 0; u < FB; ++u) {
+        const double wq = __shfl_sync(0xffffffffu, w, q0 + u);
+        const bool sel = (rowsel >> (q0 + u)) & 1u;                 // warp-uniform
 #pragma unroll
-        for (int u = 0; u < FB; ++u) {
-            int pos = __shfl_sync(0xffffffffu, kb, q0 + u);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const unsigned m = __shfl_sync(0xffffffffu, mask[c], q0 + u);
-                val[u][c] = __ldcg(a.L + pos + __popc(m & lt));
-                pres[c] |= ((m >> lane) & 1u) << u;
-                if (c + 1 < NCH) pos += __popc(m);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < FB; ++u) {
-            const double wq = __shfl_sync(0xffffffffu, w, q0 + u);
-            const bool sel = (rowsel >> (q0 + u)) & 1u;                 // warp-uniform
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-                if (sel && lane + 32 * c < cnt) tpl[(q0 + u) * cap + 32 * c] = ((pres[c] >> u) & 1u) ? wq * val[u][c] : 0.0;   // lij_dj*AAt[kk], ldlt.c:583
-        }
+        for (int c = 0; c < NCH; ++c)
+            if (sel && lane + 32 * c < cnt) tpl[(q0 + u) * cap + 32 * c] = ((pres[c] >> u) & 1u) ? wq * val[u][c] : 0.0;   // lij_dj*AAt[kk], ldlt.c:583
     }
 }
 
@@ -305,33 +312,41 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
             // ---- consumer: one register accumulator per row, the reference's additions in the reference's order
 #pragma unroll
             for (int c = 0; c < NCH; ++c) if (lane + 32 * c < cnt) kval[c] = __ldcg(&a.L[p0 + lane + 32 * c]);
-            // two ring stages per wait whenever there are two left: one flag check, one release and one pipeline
-            // fill of the shared-memory loads per 64 links instead of per 32
+            // up to kPipeMulti ring stages per wait: one flag check, one release and one pipeline fill of the shared-memory
+            // loads per kPipeMulti*32 links instead of per 32
             for (int g = 0; g < ngroups;) {
-                const int st = g % S;
-                const bool pair = g + 1 < ngroups;
-                const int st2 = (g + 1) % S;
-                while (vbk_lds_acquire(&full[st]) != g + 1) vbk_pause();
-                if (pair) { while (vbk_lds_acquire(&full[st2]) != g + 2) vbk_pause(); }
-                VBK_PTICK(0);
-                if (tracing && g == 0) a.trace[(size_t)i * 8 + 1] = vbk_globaltimer();
-                const double* tp = tile + (size_t)st * kPipeQ * cap + lane;
-                const double* tp2 = tile + (size_t)st2 * kPipeQ * cap + lane;
-                if (pair) {
+                const int left = ngroups - g;
+                if (left >= kPipeMulti && S > kPipeMulti) {
 #pragma unroll
-                    for (int q = 0; q < 2 * kPipeQ; ++q) {
+                    for (int u = 0; u < kPipeMulti; ++u) { while (vbk_lds_acquire(&full[(g + u) % S]) != g + u + 1) vbk_pause(); }
+                    VBK_PTICK(0);
+                    if (tracing && g == 0) a.trace[(size_t)i * 8 + 1] = vbk_globaltimer();
+                    {
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c)
-                            acc[c] += (q < kPipeQ ? tp[q * cap + 32 * c] : tp2[(q - kPipeQ) * cap + 32 * c]);   // temp[row] += lij_dj*AAt[kk]
+                        for (int u = 0; u < kPipeMulti; ++u) {
+                            const double* tp = tile + (size_t)((g + u) % S) * kPipeQ * cap + lane;
+#pragma unroll
+                            for (int q = 0; q < kPipeQ; ++q) {
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) acc[c] += tp[q * cap + 32 * c];      // temp[row] += lij_dj*AAt[kk]
+                            }
+                        }
                     }
+                    g += kPipeMulti;
                 } else {
+                    while (vbk_lds_acquire(&full[g % S]) != g + 1) vbk_pause();
+                    VBK_PTICK(0);
+                    if (tracing && g == 0) a.trace[(size_t)i * 8 + 1] = vbk_globaltimer();
+                    const double* tp = tile + (size_t)(g % S) * kPipeQ * cap + lane;
+                    {
 #pragma unroll
-                    for (int q = 0; q < kPipeQ; ++q) {
+                        for (int q = 0; q < kPipeQ; ++q) {
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c) acc[c] += tp[q * cap + 32 * c];      // temp[row] += lij_dj*AAt[kk]
+                            for (int c = 0; c < NCH; ++c) acc[c] += tp[q * cap + 32 * c];          // temp[row] += lij_dj*AAt[kk]
+                        }
                     }
+                    g += 1;
                 }
-                g += pair ? 2 : 1;
                 __syncwarp();
                 if (lane == 0) vbk_sts_release(&cons[0], g);
                 VBK_PTICK(1);
@@ -340,16 +355,28 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
             // ---- pivot chain (owner slice only): diagi -= lij*lij_dj in the same order (ldlt.c:573)
             if (owner) {
                 diagi = __ldcg(&a.diag[i]);
-                for (int g = 0; g < ngroups; ++g) {
-                    const int st = g % S;
-                    while (vbk_ld_volatile(&full[st]) != g + 1) vbk_pause();
-                    __threadfence_block();
-                    const double* pl = s_l + st * kPipeQ;
-                    const PipeMeta* pm = s_meta + st * kPipeQ;
+                // the producers stage the rounded products lij*(lij*dj); two ring stages per wait like the consumer --
+                // this chain is as long as the rows' chains and holds the column's last slice back if it is any slower
+                for (int g = 0; g < ngroups;) {
+                    if (ngroups - g >= kPipeMulti && S > kPipeMulti) {
 #pragma unroll
-                    for (int q = 0; q < kPipeQ; ++q) { const double p = pl[q] * pm[q].w; diagi -= p; }
+                        for (int u = 0; u < kPipeMulti; ++u) { while (vbk_lds_acquire(&full[(g + u) % S]) != g + u + 1) vbk_pause(); }
+#pragma unroll
+                        for (int u = 0; u < kPipeMulti; ++u) {
+                            const double* pl = s_l + ((g + u) % S) * kPipeQ;
+#pragma unroll
+                            for (int q = 0; q < kPipeQ; ++q) diagi -= pl[q];                       // diag[i] -= lij*lij_dj
+                        }
+                        g += kPipeMulti;
+                    } else {
+                        while (vbk_lds_acquire(&full[g % S]) != g + 1) vbk_pause();
+                        const double* pl = s_l + (g % S) * kPipeQ;
+#pragma unroll
+                        for (int q = 0; q < kPipeQ; ++q) diagi -= pl[q];
+                        g += 1;
+                    }
                     __syncwarp();
-                    if (lane == 0) vbk_st_volatile(&cons[1], g + 1);
+                    if (lane == 0) vbk_sts_release(&cons[1], g);
                 }
             }
         } else {
@@ -395,7 +422,13 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                     for (int c = 0; c < NCH; ++c) nmask[c] = a.masks[(pair0 + (size_t)gn * kPipeQ + lane) * NCH + c];
                 }
                 VBK_PTICK(3);
-                // (2) a free ring slot
+                // (2) the first batch of rows is loaded BEFORE the ring slot is waited for: once the consumer runs, a freed
+                //     slot is refilled after the stores alone, not after a round trip to the L2
+                constexpr int FB = VBK_PIPE_FB / NCH;
+                const unsigned readym = __ballot_sync(0xffffffffu, !valid || flag != 0);
+                double val[FB][NCH];
+                unsigned pres[NCH];
+                pipe_load_rows<NCH, FB>(a, kb, mask, 0, val, pres, lane);
                 if (g >= S) {
                     const int need = g - S + 1;
                     while (vbk_ld_volatile(&cons[0]) < need || (owner && vbk_ld_volatile(&cons[1]) < need)) vbk_backoff(a.backoff_ns);
@@ -410,9 +443,13 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                 //     prepared -- all of them in steady state, all but the youngest child when the task runs ahead of the
                 //     critical path -- then, as its column becomes final, what is left.  When the last child finishes only
                 //     its own rows remain to be staged.
-                const unsigned readym = __ballot_sync(0xffffffffu, !valid || flag != 0);
                 double w = lij * dj;                                   // lij_dj, ldlt.c:572
-                pipe_products<NCH>(a, w, kb, mask, tp, readym, cnt, lane);
+                pipe_store_rows<NCH, FB>(w, 0, val, pres, tp, readym, cnt, lane);
+#pragma unroll 1
+                for (int q0 = FB; q0 < kPipeQ; q0 += FB) {
+                    pipe_load_rows<NCH, FB>(a, kb, mask, q0, val, pres, lane);
+                    pipe_store_rows<NCH, FB>(w, q0, val, pres, tp, readym, cnt, lane);
+                }
                 VBK_PTICK(5);
                 if (~readym) {
                     if (valid && !flag) {
@@ -424,10 +461,13 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                     __syncwarp();
                     pipe_products_few<NCH>(a, w, kb, mask, tp, ~readym, cnt, lane);
                 }
-                s_meta[st * kPipeQ + lane].w = w;                      // the pivot chain's operands
-                s_l[st * kPipeQ + lane] = lij;
+                s_l[st * kPipeQ + lane] = lij * w;                     // the pivot chain's operand lij*lij_dj (ldlt.c:573), rounded like there
                 VBK_PTICK(6);
-                // (6) next group: first entry, readiness, lij and dj if the column is final already
+                // (6) publish the stage -- before the next group's readiness is looked at: that acquire load stalls the warp for a
+                //     round trip, which must not sit between a finished stage and its consumer
+                __syncwarp();
+                if (lane == 0) vbk_sts_release(&full[st], g + 1);
+                // (7) next group: first entry, readiness, lij and dj if the column is final already
                 int nkb = nvalid ? nk + 1 : p0, nflag = 1;
                 double nlij = 0.0, ndj = 0.0;
                 if (nvalid) {
@@ -435,9 +475,6 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
                     nflag = vbk_ld_acquire(&a.col_done[nj]);
                     if (nflag) { nlij = __ldcg(&a.L[nk]); ndj = __ldcg(&a.diag[nj]); }
                 }
-                // (7) publish the stage
-                __syncwarp();
-                if (lane == 0) vbk_sts_release(&full[st], g + 1);
                 VBK_PTICK(7);
                 if (PROF && profiling) pacc[PROF ? 14 : 0] += 1;
                 k = nk; j = nj; kb = nkb; valid = nvalid; flag = nflag; lij = nlij; dj = ndj;
