@@ -361,7 +361,7 @@ def run_batch(a, vb, lib, rank, local_rank, world):
             "parity": {"all_optimal": bool(ok), "mean_iterations": its, "max_rel_duality_gap": gap, "strict_sample": strict_sample}}
 
 
-def run_rowblock(a, vb, lib, rank, local_rank, world):
+def run_rowblock(a, vb, lib, rank, local_rank, world, partition=None):
     """BASELINE config 5: row-block smx / transpose-smx + dot / max-norm all-reduce on the synthetic multicommodity LP.
     Returns the result dict on rank 0 (None elsewhere)."""
     import torch
@@ -374,7 +374,9 @@ def run_rowblock(a, vb, lib, rank, local_rank, world):
     if True:
         lp = vb.workloads.multicommodity_lp(a.grid, a.commodities)
         kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
-        ops = vb.rowblock.RowBlockOps(lib, lp.m, lp.n, lp.kA, lp.iA, lp.A, kAt, iAt, At, dev)
+        partition = partition or a.rowblock_partition
+        coupled = partition == "coupled"
+        ops = (vb.rowblock.CoupledOps if coupled else vb.rowblock.RowBlockOps)(lib, lp.m, lp.n, lp.kA, lp.iA, lp.A, kAt, iAt, At, dev)
         rng = np.random.default_rng(1)
         x, y = rng.standard_normal(lp.n), rng.standard_normal(lp.m)
         lx, ly = ops.local_x(x), ops.local_y(y)
@@ -421,8 +423,17 @@ def run_rowblock(a, vb, lib, rank, local_rank, world):
         # parity: the distributed products against a host computation of the same sums
         import scipy.sparse as sp
         Acsr = sp.csc_matrix((lp.A, lp.iA, lp.kA), shape=(lp.m, lp.n)).tocsr()
-        rho_ref = Acsr[ops.r0:ops.r1] @ x
-        err = float(np.max(np.abs(rho.cpu().numpy()[: ops.r1 - ops.r0] - rho_ref)) / max(1.0, np.max(np.abs(rho_ref))))
+        if coupled:
+            full_ref = Acsr @ x
+            got = rho.cpu().numpy()
+            loc_ok = bool(np.array_equal(got[: ops.nl], full_ref[ops.local_rows]))          # local rows: the reference's bits
+            err = float(np.max(np.abs(got[ops.nl:] - full_ref[ops.shared_rows])) / max(1.0, np.max(np.abs(full_ref)))) if ops.ns else 0.0
+            assert loc_ok, "local rows of the coupled partition must equal the host row sums bit for bit"
+            nrow_local = ops.rows_per
+        else:
+            rho_ref = Acsr[ops.r0:ops.r1] @ x
+            err = float(np.max(np.abs(rho.cpu().numpy()[: ops.r1 - ops.r0] - rho_ref)) / max(1.0, np.max(np.abs(rho_ref))))
+            nrow_local = ops.r1 - ops.r0
         dref = float(y @ (Acsr @ x))
         derr = abs(float(d[1]) - dref) / max(1.0, abs(dref))
         assert err < 1e-12 and derr < 1e-10, (err, derr)
@@ -439,12 +450,13 @@ def run_rowblock(a, vb, lib, rank, local_rank, world):
         ms = max_over_ranks(float(sum(e0.elapsed_time(e1) for e0, e1 in ev)) / steps)
         clocks = sampler.summary()
         # e2e: host vectors in, host results out, per step
-        hx, hy = torch.from_numpy(x[ops.c0:ops.c1].copy()).pin_memory(), torch.from_numpy(y[ops.r0:ops.r1].copy()).pin_memory()
-        hrho, hsig = torch.empty(ops.r1 - ops.r0, dtype=torch.float64).pin_memory(), torch.empty(ops.c1 - ops.c0, dtype=torch.float64).pin_memory()
+        hx = torch.from_numpy(x[ops.c0:ops.c1].copy()).pin_memory()
+        hy = (ly.cpu() if coupled else torch.from_numpy(y[ops.r0:ops.r1].copy())).pin_memory()
+        hrho, hsig = torch.empty(nrow_local, dtype=torch.float64).pin_memory(), torch.empty(ops.c1 - ops.c0, dtype=torch.float64).pin_memory()
         def step_host():
-            lx[: ops.c1 - ops.c0].copy_(hx, non_blocking=True); ly[: ops.r1 - ops.r0].copy_(hy, non_blocking=True)
+            lx[: ops.c1 - ops.c0].copy_(hx, non_blocking=True); ly[:nrow_local].copy_(hy, non_blocking=True)
             d, mx = step()
-            hrho.copy_(rho[: ops.r1 - ops.r0], non_blocking=True); hsig.copy_(sig[: ops.c1 - ops.c0], non_blocking=True)
+            hrho.copy_(rho[:nrow_local], non_blocking=True); hsig.copy_(sig[: ops.c1 - ops.c0], non_blocking=True)
             return d.cpu(), mx.cpu()
         step_host(); barrier()
         t0 = time.perf_counter()
@@ -461,17 +473,22 @@ def run_rowblock(a, vb, lib, rank, local_rank, world):
                    "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                    "dtype": "f64", "data": "synthetic multicommodity LP (generator seed 1)",
                    "config": {"workload": f"BASELINE config 5: multicommodity R={a.grid} K={a.commodities}: m={lp.m} n={lp.n} nz={lp.nz}; step = A x + A^T y "
-                                          "(all-gather + row-block SpMV each, both all-gathers in flight together) + 4 dot products + 2 max-norms (ONE 48-byte all-gather)",
-                              "l2": "flushed between timed steps (256 MiB write)", "launch": graphed,
-                              "parallelism": f"row blocks over {world} rank(s); NCCL all-gather of x, y and of the 6 partial scalars"},
+                                          + ("(column blocks; rows local to a rank or shared: one all-reduce of the shared rows' partial sums, no vector travels) "
+                                             "+ 4 dot products + 2 max-norms (ONE 72-byte all-gather)" if coupled else
+                                             "(all-gather + row-block SpMV each, both all-gathers in flight together) + 4 dot products + 2 max-norms (ONE 48-byte all-gather)"),
+                              "partition": partition, "l2": "flushed between timed steps (256 MiB write)", "launch": graphed,
+                              "parallelism": (f"column blocks over {world} rank(s); {ops.ns} shared rows of {lp.m}: NCCL all-reduce of {8 * ops.ns} bytes per step" if coupled else
+                                              f"row blocks over {world} rank(s); NCCL all-gather of x, y and of the 6 partial scalars")},
                    "e2e": {"value": total_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
-                           "h2d_bytes_per_step": int(8 * (ops.c1 - ops.c0 + ops.r1 - ops.r0)),
-                           "d2h_bytes_per_step": int(8 * (ops.c1 - ops.c0 + ops.r1 - ops.r0) + 48)},
+                           "h2d_bytes_per_step": int(8 * (ops.c1 - ops.c0 + nrow_local)),
+                           "d2h_bytes_per_step": int(8 * (ops.c1 - ops.c0 + nrow_local) + 48)},
                    "gpu_launches": 5 * steps, "clocks": clocks,
                    "roofline": {"kernel": "k_spmv_rows + k_dot_partial/k_absmax_partial (whole step)", "bound": "hbm",
                                 "achieved": v / world, "peak": hbm, "unit": "GB/s", "frac": v / world / hbm, "traffic": None,
                                 "note": "per-GPU algorithmic bytes (12 B per nonzero, 8 B per vector entry read or written) over the step time, collectives included"},
-                   "parity": {"max_rel_err_Ax": err, "rel_err_dot": derr}}
+                   "parity": ({"local_rows_bit_identical": True, "max_rel_err_Ax_shared_rows": err, "rel_err_dot": derr,
+                               "note": "A^T y and the local rows of A x keep the reference's summation order; the shared rows are re-associated by column block"}
+                              if coupled else {"max_rel_err_Ax": err, "rel_err_dot": derr})}
             return out
     return None
 
@@ -506,6 +523,9 @@ def main():
                     help="batch workload: arithmetic mode (fast: tolerance parity, all LPs checked optimal + one strict sample)")
     ap.add_argument("--batch-steps", type=int, default=1)
     ap.add_argument("--rowblock-steps", type=int, default=20)
+    ap.add_argument("--rowblock-partition", default="rows", choices=["rows", "coupled"],
+                    help="rowblock workload: 'rows' = equal row blocks + all-gather of x and y (bit-identical smx); 'coupled' = column blocks, "
+                         "rows local to a rank or shared, one all-reduce of the shared rows' partial sums")
     ap.add_argument("--no-graph", action="store_true", help="row-block workload: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="batch workload: LPs per GPU per step (default: 2 per solver stream, at least 8)")
     ap.add_argument("--batch-m", type=int, default=2000)
@@ -883,10 +903,14 @@ def main():
         sb = run_batch(a, vb, lib, rank, local_rank, world)
         dist.barrier()
         a.rowblock_steps = max(a.rowblock_steps, 10)
-        sr = run_rowblock(a, vb, lib, rank, local_rank, world)
+        sr = run_rowblock(a, vb, lib, rank, local_rank, world, partition="rows")
+        dist.barrier()
+        sc = run_rowblock(a, vb, lib, rank, local_rank, world, partition="coupled")
         if rank == 0:
-            out["sharded"] = {"batch": sb, "rowblock": sr,
-                              "note": "BASELINE configs 4 and 5 on the same N ranks; the primary metric above is N independent replicas of the KKT step"}
+            out["sharded"] = {"batch": sb, "rowblock": sr, "rowblock_coupled": sc,
+                              "note": "BASELINE configs 4 and 5 on the same N ranks; the primary metric above is N independent replicas of the KKT step. "
+                                      "rowblock = equal row blocks, x and y all-gathered (bit-identical smx); rowblock_coupled = column blocks with the "
+                                      "coupling rows' partial sums all-reduced (fast-mode variant: those rows are re-associated)"}
     if rank == 0:
         print(json.dumps(out))
     if dist:

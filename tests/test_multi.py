@@ -92,6 +92,64 @@ def test_rowblock_smx_dot_maxv_gloo(tmp_path, emu_lib, oracle_lib, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def _coupled_worker(rank, world, port, out):
+    vb, dist = _init(rank, world, port)
+    try:
+        import torch
+        lib = vb.load(EMU)
+        lp = vb.workloads.multicommodity_lp(4, 5)          # 5 commodities on a 4 x 4 grid: conservation rows per commodity, 48 coupling rows
+        kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+        ops = vb.rowblock.CoupledOps(lib, lp.m, lp.n, lp.kA, lp.iA, lp.A, kAt, iAt, At, "cpu")
+        rng = np.random.default_rng(11)
+        x, y = rng.standard_normal(lp.n), rng.standard_normal(lp.m)
+        rho = torch.zeros(ops.rows_per, dtype=torch.float64)
+        sig = torch.zeros(ops.cols_per, dtype=torch.float64)
+        sums, maxes = ops.step(ops.local_x(x), ops.local_y(y), rho, sig)
+        np.savez(out + f".{rank}.npz", rho=rho.numpy().copy(), sig=sig.numpy()[: ops.c1 - ops.c0].copy(), c=np.array([ops.c0, ops.c1]),
+                 local_rows=ops.local_rows, shared_rows=ops.shared_rows, sums=sums.numpy().copy(), maxes=maxes.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_coupled_partition_gloo(tmp_path, vbkkt, emu_lib, oracle_lib, world):
+    """The structure-following partition (CoupledOps): local rows of A x and all of A^T y are BIT-identical to the
+    oracle's smx, the shared (coupling) rows agree to rounding (their sums are re-associated by column block), every
+    row is local to exactly one rank or shared, and all ranks hold the same six scalars."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "cp")
+    mp.spawn(_coupled_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    lp = vbkkt.workloads.multicommodity_lp(4, 5)
+    rng = np.random.default_rng(11)
+    x, y = rng.standard_normal(lp.n), rng.standard_normal(lp.m)
+    kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    rho_ref, sig_ref = np.zeros(lp.m), np.zeros(lp.n)
+    oracle_lib.kko_smx(lp.m, lp.n, H.ptr_d(lp.A), H.ptr_i(lp.kA), H.ptr_i(lp.iA), H.ptr_d(x), H.ptr_d(rho_ref))
+    oracle_lib.kko_smx(lp.n, lp.m, H.ptr_d(At), H.ptr_i(kAt), H.ptr_i(iAt), H.ptr_d(y), H.ptr_d(sig_ref))
+    zs = [np.load(out + f".{r}.npz") for r in range(world)]
+    covered = np.zeros(lp.m, dtype=int)
+    sig = np.zeros(lp.n)
+    shared = zs[0]["shared_rows"]
+    assert 0 < len(shared) < lp.m // 2
+    covered[shared] += 1
+    for z in zs:
+        lr = z["local_rows"]
+        covered[lr] += 1
+        assert np.array_equal(z["shared_rows"], shared)
+        assert np.array_equal(z["rho"][: len(lr)], rho_ref[lr])                                    # local rows: the reference's bits
+        assert np.allclose(z["rho"][len(lr):], rho_ref[shared], rtol=1e-13, atol=1e-13)           # coupling rows: re-associated
+        assert np.array_equal(z["rho"][len(lr):], zs[0]["rho"][len(zs[0]["local_rows"]):])        # ... but the same on every rank
+        c0, c1 = z["c"]
+        sig[c0:c1] = z["sig"]
+        assert np.array_equal(z["sums"], zs[0]["sums"]) and np.array_equal(z["maxes"], zs[0]["maxes"])
+    assert np.all(covered == 1)
+    assert np.array_equal(sig, sig_ref)                                                            # A^T y: bit-identical
+    ref = np.array([x @ sig_ref, y @ rho_ref, rho_ref @ rho_ref, sig_ref @ sig_ref])
+    assert np.allclose(zs[0]["sums"], ref, rtol=1e-12, atol=1e-12)
+    assert np.isclose(zs[0]["maxes"][0], np.abs(rho_ref).max(), rtol=1e-13) and zs[0]["maxes"][1] == np.abs(sig_ref).max()
+
+
+# ------------------------------------------------------------------------------------------------
 def _tiny_lp(vb, i):
     return vb.workloads.random_sparse_lp(seed=i, m=12, n=20, nnz_per_col=3)
 
