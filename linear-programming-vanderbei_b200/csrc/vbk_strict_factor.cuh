@@ -15,14 +15,18 @@
 //   producer warps   form the products of 32 contributors at a time into a ring of shared-memory
 //                    tiles tile[stage][q][slot] -- row q holds contributor q's products for every row
 //                    of the task, +0.0 where the contributor has no entry (adding +0.0 is exact and the
-//                    accumulator is never -0.0).  They wait per CONTRIBUTOR for its column to be final
-//                    (col_done[j]), so everything except the products of the last child is staged
-//                    before that child finishes;
+//                    accumulator is never -0.0).  Which rows a contributor holds is a precomputed bit
+//                    mask per (task, contributor) pair (k_pipe_masks), so every row costs the same few
+//                    instructions.  They wait per CONTRIBUTOR for its column to be final (col_done[j]),
+//                    so everything except the products of the last child is staged before that child
+//                    finishes;
 //   consumer warp    one lane per row of the task (up to 4 rows per lane when row blocks are wider
 //                    than 32): the accumulator lives in a register, a ring stage is 32 back-to-back
-//                    dependent additions per lane, in the reference's order;
+//                    dependent additions per lane, in the reference's order, kPipeMulti stages per
+//                    flag check;
 //   pivot warp       (pivot-owning slice only) the diagonal's own chain diagi -= lij*(lij*dj)
-//                    (ldlt.c:573) from the staged (lij, lij*dj) pairs.
+//                    (ldlt.c:573) from the staged products, with the consumer's loop: this chain is as
+//                    long as the rows' chains and must not be any slower.
 //
 // Tasks are (column, 32-row block) slices as before (vbk_symbolic.h), claimed in index order by
 // persistent CTAs.  The LAST slice of a column owns the pivot: the other slices publish their
@@ -81,18 +85,14 @@ struct PipeArgs {
     long long* trace;
 };
 
-// what a producer stages per contributor besides the products: lij*dj, the first entry of column j in the rows of the
-// task and how many there are (16 bytes: one broadcast LDS.128 per use)
-struct alignas(16) PipeMeta { double w; int kb; int len; };
-
 // bytes of dynamic shared memory the kernel needs
 inline size_t pipe_smem_bytes(int cap, int nstages, int rowblk, int nwarps)
 {
+    (void)rowblk;
     size_t d = (size_t)nstages * kPipeQ * cap      // product tiles
-             + (size_t)2 * nstages * kPipeQ        // PipeMeta per staged contributor
-             + (size_t)nstages * kPipeQ            // lij per staged contributor
+             + (size_t)nstages * kPipeQ            // lij*(lij*dj) per staged contributor (the pivot chain's operands)
              + (size_t)cap + nwarps + 2;           // undivided column, per-warp max, pivot
-    size_t i = (size_t)nstages + 2 + cap + rowblk + 8;
+    size_t i = (size_t)nstages + 2 + 8;
     return d * sizeof(double) + i * sizeof(int);
 }
 
@@ -255,16 +255,13 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int P = nwarps - 2;                                   // producer warps
     double* tile = reinterpret_cast<double*>(raw);              // [S][kPipeQ][cap]
-    PipeMeta* s_meta = reinterpret_cast<PipeMeta*>(tile + (size_t)S * kPipeQ * cap);   // [S][kPipeQ]
-    double* s_l = reinterpret_cast<double*>(s_meta + S * kPipeQ);                       // [S][kPipeQ]
+    double* s_l = tile + (size_t)S * kPipeQ * cap;              // [S][kPipeQ] lij*(lij*dj) of the staged contributors
     double* temp = s_l + S * kPipeQ;                            // [cap] undivided entries of the task
     double* s_red = temp + cap;                                 // [nwarps]
     double* s_dbl = s_red + nwarps;                             // [0] pivot, [1] diagonal chain result
     int* full = reinterpret_cast<int*>(s_dbl + 2);              // [S] group number + 1 staged in the slot
     int* cons = full + S;                                       // [0] groups consumed by the rows, [1] by the pivot chain
-    int* rows = cons + 2;                                       // [cap] row indices of the task, padded with INT_MAX
-    int* blockmap = rows + cap;                                 // [rowblk] row-in-block -> slot
-    int* s_ctl = blockmap + a.rowblk;                           // [0] task, [1] keep
+    int* s_ctl = cons + 2;                                      // [0] task, [1] keep
 
     const double thresh = a.epsnum * bits_to_double(a.scal_bits[S_MAXDIAG]);     // ldlt.c:600
     const int wstride = a.nblk + 1;
@@ -284,7 +281,6 @@ static __global__ void __launch_bounds__(kPipeWarpsDefault * 32) k_factor_pipe(P
         const int i = a.task_col[t], blk = a.task_blk[t], p0 = a.task_pos0[t], cnt = a.task_cnt[t];
         const int nslices = a.col_ntask[i];
         const bool owner = (t == a.col_task0[i] + nslices - 1);
-        const int bs = a.slice_row0 + (blk < 0 ? 0 : blk) * a.rowblk;             // first row of the block
         const int rb = a.rowptr[i], re = a.rowptr[i + 1];
         const int ngroups = (re - rb + kPipeQ - 1) / kPipeQ;
 
