@@ -735,7 +735,9 @@ def main():
     assert np.array_equal(wy.numpy(), sol_y), "host-buffer path and device-pointer path disagree"
     e2e = {"value": world * flops_step / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(8 * N + 2 * 16 * N), "d2h_bytes_per_step": int(2 * 8 * N),
-           "api": "ldltfac + 2 x forwardbackward (the reference's plugin symbols, src/ipo/ldlt.h:1-20), pinned host arrays"}
+           "api": ("ldltfac + 2 x forwardbackward (the reference's plugin symbols, src/ipo/ldlt.h:1-20), pinned host arrays; the library "
+                   "solves the iteration's constant second right-hand side speculatively with the first call's sweeps and answers the "
+                   "second call from that result when its inputs are bit-identical ($VBK_SPECULATE=0: 181 ms)")}
 
     def rank0_line():
         cpu = None
