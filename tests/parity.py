@@ -210,3 +210,40 @@ def check_fast_sparse_columns(vbkkt, lib, oracle, lp, method, it):
     finally:
         F.close()
         K.close()
+
+
+def check_b1_speculation(lib, oracle, lp, rounds=4):
+    """The reference's call sequence on the B1 symbols -- ldltfac, forwardbackward(f), forwardbackward(g) with g = (-b, -c)
+    every round (hsd.c:218-228) -- against the oracle, call by call, bit for bit; round 2 asks for a different g than the one
+    the library remembered, so a stale speculative answer would show."""
+    import ctypes as C
+    kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    lib.ldltfac.argtypes = [C.c_int, C.c_int, H.c_int_p, H.c_int_p, H.c_double_p, H.c_double_p, H.c_double_p,
+                            H.c_int_p, H.c_int_p, H.c_double_p, C.c_int]
+    lib.ldltfac.restype = None
+    lib.forwardbackward.argtypes = [H.c_double_p] * 4
+    lib.forwardbackward.restype = None
+    lib.inv_clo.restype = None
+    lib.inv_clo()
+    F = H.oracle_factor_for(oracle, lp)
+    rng = np.random.default_rng(5)
+    gy0, gx0 = -lp.b.copy(), -lp.c.copy()
+    try:
+        for it in range(rounds):
+            E = 10.0 ** rng.uniform(-2, 2, lp.m)
+            D = 10.0 ** rng.uniform(-2, 2, lp.n)
+            lib.ldltfac(lp.n, lp.m, H.ptr_i(kAt), H.ptr_i(iAt), H.ptr_d(At), H.ptr_d(E), H.ptr_d(D),
+                        H.ptr_i(lp.kA), H.ptr_i(lp.iA), H.ptr_d(lp.A), 0)
+            F.factor(E, D)
+            fy, fx = rng.standard_normal(lp.m), rng.standard_normal(lp.n)
+            gy, gx = (gy0.copy(), gx0.copy()) if it != 2 else (gy0 * 1.5, gx0 * 0.5)
+            oy, ox, _ = F.solve(E, D, fy, fx)
+            o2y, o2x, _ = F.solve(E, D, gy, gx)
+            lib.forwardbackward(H.ptr_d(E), H.ptr_d(D), H.ptr_d(fy), H.ptr_d(fx))
+            lib.forwardbackward(H.ptr_d(E), H.ptr_d(D), H.ptr_d(gy), H.ptr_d(gx))
+            assert np.array_equal(fy, oy) and np.array_equal(fx, ox), it
+            assert np.array_equal(gy, o2y) and np.array_equal(gx, o2x), it
+    finally:
+        F.close()
+        lib.inv_clo()
+

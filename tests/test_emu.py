@@ -95,3 +95,11 @@ def test_emu_full_solve_hsdls(vbkkt, emu_lib, name):
     search (hsdls.c:296-336) with the reference's MIN-fold semantics, constant delta, its own status rules -- prints
     the compiled reference's log byte for byte and returns bit-equal x and y."""
     assert P.check_hsdls(vbkkt, emu_lib, H.load_fixture(name)) == 0
+
+
+def test_emu_b1_speculative_second_rhs(vbkkt, emu_lib, oracle_lib):
+    """Seam B1 (ldltfac + two forwardbackward calls per factorisation, hsd.c:218-228): from the second factorisation on the
+    library solves the remembered second right-hand side together with the first call and answers the second call from
+    that result -- which must be exactly what the oracle computes for each call, also when the second right-hand side
+    turns out to differ from the remembered one."""
+    P.check_b1_speculation(emu_lib, oracle_lib, H.load_fixture("afiro"))

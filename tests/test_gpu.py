@@ -263,6 +263,13 @@ def test_factor_residual_property(vbkkt, gpu_lib):
     K.close()
 
 
+@pytest.mark.parametrize("name", ["afiro", "25fv47"])
+def test_b1_speculative_second_rhs(vbkkt, gpu_lib, oracle_lib, name):
+    """The B1 symbols answer the second forwardbackward call of a factorisation from a speculative solve (csrc/vbk_capi.cu:
+    b1_solve): every call must return the oracle's bits, also when the speculation misses."""
+    P.check_b1_speculation(gpu_lib, oracle_lib, H.load_fixture(name))
+
+
 def test_b1_seam_reference_method_on_gpu_plugins(vbkkt, gpu_lib):
     """The drop-in itself: the reference's UNMODIFIED METHOD object (hsd.c compiled in oracle/_ref)
     linked against libvbkkt.so's ldltfac/forwardbackward/smx/atnum/dotprod/maxv reproduces the
