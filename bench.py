@@ -567,6 +567,33 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
+        if a.gpus > 1 and not os.environ.get("VBK_BENCH_REF_CHILD"):
+            # the config is N independent replicas: the (single-threaded) reference runs N of them side by side, one host
+            # core each, as separate processes (it keeps ONE factor object per process, ldlt.c:108-120)
+            env = dict(os.environ, VBK_BENCH_REF_CHILD="1")
+            for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE", "TORCHELASTIC_RUN_ID"):
+                env.pop(k, None)
+            cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", str(a.steps), "--warmup", str(a.warmup),
+                   "--workload", a.workload, "--iterate", str(a.iterate)]
+            kids = [subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(a.gpus)]
+            lines = []
+            for kproc in kids:
+                out_k, _ = kproc.communicate()
+                rows = [ln for ln in out_k.splitlines() if ln.startswith("{")]
+                if kproc.returncode != 0 or not rows:
+                    raise SystemExit("bench.py --impl reference: a replica process failed")
+                lines.append(json.loads(rows[-1]))
+            dt = max(r["ms_per_step"] for r in lines) * 1e-3
+            flops = lines[0]["flops_per_step"]
+            v = a.gpus * flops / dt / 1e9
+            one = lines[0]
+            one.update({"value": v, "n_gpus": a.gpus, "ms_per_step": dt * 1e3, "config": config,
+                        "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": a.gpus, "kind": one["cpu_baseline"]["kind"],
+                                         "sample": f"{a.gpus} replicas side by side (one process and one host core each), {one['steps']} KKT steps each, "
+                                                   f"slowest replica {dt * 1e3:.2f} ms/step"},
+                        "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            print(json.dumps(one))
+            return
         cpu = CpuKkt(lp)                                         # nothing of the product on this arm
         t0 = time.perf_counter()
         sol_y, sol_x = cpu.step(it)
