@@ -242,6 +242,30 @@ def test_rowblock_ops_on_one_gpu(vbkkt, gpu_lib, oracle_lib, name):
     torch.cuda.synchronize()
 
 
+def test_coupled_partition_on_one_gpu(vbkkt, gpu_lib, oracle_lib):
+    """rowblock.CoupledOps on the device (world size 1: every row is local): A x and A^T y equal the oracle's smx bit for
+    bit, the six scalars of the step agree with the host's."""
+    import torch
+    lp = vbkkt.workloads.multicommodity_lp(6, 4)
+    kAt, iAt, At = H.transpose_csc(lp.m, lp.n, lp.kA, lp.iA, lp.A)
+    ops = vbkkt.rowblock.CoupledOps(gpu_lib, lp.m, lp.n, lp.kA, lp.iA, lp.A, kAt, iAt, At, "cuda:0")
+    rng = np.random.default_rng(3)
+    x, y = rng.standard_normal(lp.n), rng.standard_normal(lp.m)
+    rho = torch.zeros(ops.rows_per, dtype=torch.float64, device="cuda:0")
+    sig = torch.zeros(ops.cols_per, dtype=torch.float64, device="cuda:0")
+    sums, maxes = ops.step(ops.local_x(x), ops.local_y(y), rho, sig)
+    torch.cuda.synchronize()
+    rho_ref, sig_ref = np.zeros(lp.m), np.zeros(lp.n)
+    oracle_lib.kko_smx(lp.m, lp.n, H.ptr_d(lp.A), H.ptr_i(lp.kA), H.ptr_i(lp.iA), H.ptr_d(x), H.ptr_d(rho_ref))
+    oracle_lib.kko_smx(lp.n, lp.m, H.ptr_d(At), H.ptr_i(kAt), H.ptr_i(iAt), H.ptr_d(y), H.ptr_d(sig_ref))
+    got = rho.cpu().numpy()
+    assert ops.ns == 0 and np.array_equal(got[: ops.nl], rho_ref[ops.local_rows])
+    assert np.array_equal(sig.cpu().numpy()[: lp.n], sig_ref)
+    ref = np.array([x @ sig_ref, y @ rho_ref, rho_ref @ rho_ref, sig_ref @ sig_ref])
+    assert np.allclose(sums.cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+    assert maxes.cpu().numpy()[0] == np.abs(rho_ref).max() and maxes.cpu().numpy()[1] == np.abs(sig_ref).max()
+
+
 def test_factor_residual_property(vbkkt, gpu_lib):
     """Size-independent property at a size the oracle is not needed for: K z = rhs after
     forwardbackward, measured with scipy (|r| small relative to |rhs|)."""
