@@ -142,6 +142,7 @@ private:
     // slice tasks of the numeric factorisation (vbk_symbolic.h) and the strict factor kernel's hand-off state
     // (vbk_strict_factor.cuh): producer/consumer pipeline per slice task
     DevArray<int> task_col_, task_blk_, task_pos0_, task_cnt_, col_task0_, col_ntask_, winptr_;
+    double schur_mean_tail_ = 0.0;             // fast mode: mean tail length of the Schur assembly's contributors
     DevArray<unsigned> pipe_masks_;            // presence masks of the (task, contributor) pairs (k_pipe_masks)
     DevArray<long long> task_pair0_;           // [ntasks] first pair of a task
     void fill_pipe_args(struct PipeArgs& pa, int ntasks);

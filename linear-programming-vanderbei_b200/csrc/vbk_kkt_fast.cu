@@ -39,6 +39,14 @@ void Kkt::prepare_fast()
             spend[(size_t)(i - T)] = sym_.rowptr[i] + (int)(std::lower_bound(b, e, T) - b);
         }
         sp_end_.upload(spend, stream_);
+        // mean length of the tails the Schur assembly walks (entries of a sparse contributor below the window row)
+        double tails = 0.0, contributors = 0.0;
+        for (int i = T; i < N; ++i)
+            for (int t = sym_.rowptr[i]; t < spend[(size_t)(i - T)]; ++t) {
+                tails += sym_.kL[sym_.rj_asc[t] + 1] - sym_.rk_asc[t] - 1;
+                contributors += 1.0;
+            }
+        schur_mean_tail_ = contributors > 0 ? tails / contributors : 0.0;
         // etree levels of the sparse columns (parent restricted to j < T): every level is one launch of
         // k_sparse_level for its light columns and one of k_sparse_level_heavy for the heavy ones
         // (vbk_sparse_level.cuh).  weight of a column = entries its contributors' tails apply to it
@@ -69,7 +77,8 @@ void Kkt::prepare_fast()
     }
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_sparse_level_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
-    VBK_CUDA(cudaFuncSetAttribute(k_schur_window2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_schur_window2<kSchur2ThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
+    VBK_CUDA(cudaFuncSetAttribute(k_schur_window2<kSchur2ThreadsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_));
     VBK_CUDA(cudaFuncSetAttribute(k_window_tinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTinvSmem));
     VBK_CUDA(cudaFuncSetAttribute(k_window_tri3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriV3Smem));
     VBK_CUDA(cudaFuncSetAttribute(k_dense_update_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -159,7 +168,16 @@ void Kkt::factor_window_fast()
     //    Entries outside the fill pattern are never written: start from zero.
     VBK_CUDA(cudaMemsetAsync(Sw_.p, 0, sizeof(double) * (size_t)W * W, stream_));
     {
-        const size_t sc2_smem = sizeof(double) * ((size_t)W + 2 * kSchur2Batch) + sizeof(int) * 2 * kSchur2Batch;
+        // long tails (large multicommodity LPs: ~1100 entries per contributor on average) want many threads per CTA, short
+        // ones few (measured: R=50/K=40 961 -> 480 ms per factorisation with 1024 threads, R=32/K=25 and dfl001 ~10 % slower); $VBK_SCHUR_THREADS=small|large pins the choice
+        bool large = schur_mean_tail_ >= 768.0;
+        if (const char* e = std::getenv("VBK_SCHUR_THREADS")) large = std::string(e) == "large";
+        const int nt = large ? kSchur2ThreadsLarge : kSchur2ThreadsSmall;
+        size_t sc2_smem = sizeof(double) * ((size_t)W + 2 * nt) + sizeof(int) * 2 * nt;
+        if (sc2_smem > (size_t)smem_optin_ && large) {
+            large = false;
+            sc2_smem = sizeof(double) * ((size_t)W + 2 * kSchur2ThreadsSmall) + sizeof(int) * 2 * kSchur2ThreadsSmall;
+        }
         if (sc2_smem > (size_t)smem_optin_) {
             std::fprintf(stderr, "vbkkt: dense window of %d columns exceeds the Schur assembly's shared memory\n", W);
             std::exit(1);
@@ -167,7 +185,8 @@ void Kkt::factor_window_fast()
         Schur2Args sc;
         sc.N = N; sc.T = T; sc.ld = W; sc.cap = W; sc.kL = kL_.p; sc.iL = iL_.p; sc.L = L_.p; sc.diag = diag_.p;
         sc.rowptr = rowptr_.p; sc.rk = rk_asc_.p; sc.rj = rj_asc_.p; sc.spend = sp_end_.p; sc.S = Sw_.p; sc.wmag = wmag_.p;
-        VBK_LAUNCH(k_schur_window2, std::min(W, num_sms_ * 6), kSchur2Threads, sc2_smem, stream_, sc);
+        if (large) VBK_LAUNCH(k_schur_window2<kSchur2ThreadsLarge>, std::min(W, num_sms_ * 6), kSchur2ThreadsLarge, sc2_smem, stream_, sc);
+        else       VBK_LAUNCH(k_schur_window2<kSchur2ThreadsSmall>, std::min(W, num_sms_ * 6), kSchur2ThreadsSmall, sc2_smem, stream_, sc);
     }
 
     // 3. blocked right-looking dense LDL^T of the window: 128-column panels (vbk_dense_panel.cuh) -- diagonal block,

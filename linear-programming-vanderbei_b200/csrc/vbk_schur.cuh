@@ -8,12 +8,15 @@
 namespace vbk {
 
 // Schur assembly of one window column per CTA.  S need not be zeroed for the rows >= i of column i (all are written).
+// NT threads per CTA = contributor records per staged batch.  Every thread holds two entries of each of the next four
+// tails in flight, so tails of up to 2*NT entries never take an unprefetched trip to the L2: 256 threads for the
+// small windows of the netlib LPs, 1024 for the long tails (~1000 entries) of the large multicommodity LPs.
 #ifdef VBK_EMU
-constexpr int kSchur2Threads = 64;
-constexpr int kSchur2Batch = 64;
+constexpr int kSchur2ThreadsSmall = 64;
+constexpr int kSchur2ThreadsLarge = 128;
 #else
-constexpr int kSchur2Threads = 256;
-constexpr int kSchur2Batch = 256;
+constexpr int kSchur2ThreadsSmall = 256;
+constexpr int kSchur2ThreadsLarge = 1024;
 #endif
 struct Schur2Args {
     int N, T, ld, cap;                 // cap: doubles of shared memory for the column image
@@ -23,8 +26,10 @@ struct Schur2Args {
     double* S; double* wmag;
 };
 
-static __global__ void __launch_bounds__(kSchur2Threads) k_schur_window2(Schur2Args a)
+template <int NT>
+static __global__ void __launch_bounds__(NT) k_schur_window2(Schur2Args a)
 {
+    constexpr int kSchur2Threads = NT, kSchur2Batch = NT;
     VBK_DYN_SMEM(raw);
     double* acc = reinterpret_cast<double*>(raw);                         // [cap]
     double* sw = acc + a.cap;                                             // [batch] L_ij d_j
