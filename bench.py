@@ -274,7 +274,7 @@ def multi_gpu_workload(a, rank, local_rank, world):
                               "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    lib = vb.load()
+    lib = vb.load(os.environ.get("VBK_LIB"))
     if lib.vbk_device_count() < 1 or not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -629,7 +629,7 @@ def main():
     # ------------------------------------------------------------------ our arm (GPU)
     import torch
     vb = _load("vbkkt", ROOT / "linear-programming-vanderbei_b200" / "__init__.py")
-    lib = vb.load()
+    lib = vb.load(os.environ.get("VBK_LIB"))
     if lib.vbk_device_count() < 1 or not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the KKT path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)

@@ -20,12 +20,15 @@ namespace vbk {
 // (compiled for the host thread emulator too -- tests/test_emu.py checks the bit-exactness claim on the CPU -- with
 // smaller CTAs: every emulated thread is an OS thread)
 constexpr int kSpWarps = 4;
+#ifndef VBK_SP_HEAVY_THREADS
+#define VBK_SP_HEAVY_THREADS 1024
+#endif
 #ifdef VBK_EMU
 constexpr int kSpHeavyThreads = 64;
 constexpr int kSpHeavyBatch = 64;
 #else
-constexpr int kSpHeavyThreads = 512;
-constexpr int kSpHeavyBatch = 512;
+constexpr int kSpHeavyThreads = VBK_SP_HEAVY_THREADS;
+constexpr int kSpHeavyBatch = VBK_SP_HEAVY_THREADS;
 #endif
 
 struct SparseLevelArgs {
