@@ -59,6 +59,22 @@ def test_symbolic_is_bit_exact(vbkkt, product_lib, name):
     k.close()
 
 
+def test_pattern_rebuilt_from_cached_ordering_on_every_fixture(vbkkt, product_lib, tmp_path, monkeypatch):
+    """Symbolic::pattern_from_ordering (the path a cached ordering takes, vbk_symbolic.cpp): for every committed netlib
+    fixture the second analysis -- ordering read from $VBK_SYM_CACHE, fill pattern rebuilt by the elimination-tree pass --
+    gives the reference's kAAt and iAAt (sha256 stored with the fixture)."""
+    monkeypatch.setenv("VBK_SYM_CACHE", str(tmp_path))
+    for name in H.fixture_names():
+        lp = H.load_fixture(name)
+        for _ in range(2):
+            k = H.kkt_for(vbkkt, product_lib, lp, device=-1)
+            kA, iL = k.kAAt, k.iAAt.astype(np.int32)
+            k.close()
+        assert np.array_equal(kA, lp.extra["sym_kAAt"]), name
+        assert hashlib.sha256(iL.tobytes()).hexdigest() == str(lp.extra["sym_iAAt_sha256"]), name
+    assert len(list(tmp_path.glob("vbksym_*.bin"))) == len(H.fixture_names())
+
+
 def test_numeric_call_without_gpu_fails_loudly(vbkkt, product_lib):
     """No CPU fallback: on a box without a CUDA device a numeric entry point terminates the process
     with a message (run in a child so the test process survives)."""
