@@ -90,13 +90,14 @@ static __global__ void __launch_bounds__(kSolveThreads) k_fwd_flags(FlagSolveArg
             if (t0 + 32 + lane < re) { nj = a.rj[t0 + 32 + lane]; nl = a.L[a.rk[t0 + 32 + lane]]; }
             // Wait for the batch's columns.  Every lane looks at its flag once; then only the lane with the smallest
             // unfinished column spins (a row of the dense tail waits for the next 32 columns of the chain: 32 spinning
-            // lanes in each of thousands of warps would saturate the L2 with polls), the others re-check when it is done.
+            // lanes in each of thousands of warps would saturate the L2 with polls), the others follow one by one.
             unsigned pending = __ballot_sync(0xffffffffu, j >= 0 && vbk_ld_volatile(&a.done[j]) == 0);
             while (pending) {
                 const int first = __ffs(pending) - 1;
                 if (lane == first) { while (vbk_ld_volatile(&a.done[j]) == 0) __nanosleep(20); }
                 __syncwarp();
-                pending = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && lane != first && vbk_ld_volatile(&a.done[j]) == 0);
+                pending &= pending - 1;          // the others are not looked at again here: each gets its own turn (its first
+                                                 // poll is the check), which keeps a round trip off the chain of the dense tail
             }
             // z[j] is read only after its flag has been seen set (control dependency) and bypasses L1; the writer
             // released z before raising the flag
