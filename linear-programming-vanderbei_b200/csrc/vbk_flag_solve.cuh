@@ -137,7 +137,8 @@ static __global__ void __launch_bounds__(kSolveThreads) k_bwd_flags(FlagSolveArg
         const int par = a.parent[i];
         if (lane == 0 && par >= 0 && par < a.nclaim) {   // columns >= nclaim were solved before this launch
             while (vbk_ld_volatile(&a.done[par]) == 0) __nanosleep(20);
-            __threadfence();
+            // z of the finished rows is read below with __ldcg, after this poll has returned (control dependency): the
+            // volatile-flag hand-off of k_bwd_pipe, no reader-side fence
         }
         __syncwarp();
         double beta = a.z[i];                        // z[i] after the diagonal sweep (previous launch)
@@ -198,7 +199,7 @@ static __global__ void __launch_bounds__(kSolveThreads) k_bwd_flags(FlagSolveArg
             else a.z[i] = 0.0;
         }
         if (lane == 0) {
-            __threadfence();
+            vbk_fence_release();
             atomicExch(&a.done[i], 1);
         }
         __syncwarp();
