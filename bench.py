@@ -327,8 +327,10 @@ def run_batch(a, vb, lib, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     res = None
+    batch_launches = 0
     for _ in range(a.batch_steps):
         res = vb.batch.solve_local(lib, mine, "hsd", local_rank, mode, a.streams)
+        batch_launches += int(lib.vbk_batch_launches())
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.summary()
@@ -357,7 +359,8 @@ def run_batch(a, vb, lib, rank, local_rank, world):
             "e2e": {"value": v, "unit": "LP/s", "h2d_bytes_per_step": int(nbytes_in),
                     "d2h_bytes_per_step": int(sum(8 * (lp.m + lp.n) for lp in mine)),
                     "note": "vbk_solve_batch takes host arrays and returns host x,y: the timed region is end to end, symbolic phase included"},
-            "gpu_launches": None, "clocks": clocks,
+            "gpu_launches": batch_launches, "gpu_launches_note": "rank 0's kernels inside the timed region (vbk_batch_launches)",
+            "clocks": clocks,
             "parity": {"all_optimal": bool(ok), "mean_iterations": its, "max_rel_duality_gap": gap, "strict_sample": strict_sample}}
 
 

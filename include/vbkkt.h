@@ -158,6 +158,8 @@ typedef struct vbk_lp_desc {
 } vbk_lp_desc;
 /* method: 0 = hsd, 1 = intpt, 2 = hsdls.  Returns the number of LPs whose status is not 0. */
 int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp_desc *lps, int nstreams);
+/* kernels launched by all LPs of the last vbk_solve_batch call of this process */
+long long vbk_batch_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-block partitioned smx / dotprod / maxv (BASELINE.json config 5): the per-rank pieces.  Device

@@ -28,6 +28,8 @@ class LpDesc(C.Structure):
 def declare(lib):
     lib.vbk_solve_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(LpDesc), C.c_int]
     lib.vbk_solve_batch.restype = C.c_int
+    lib.vbk_batch_launches.argtypes = []
+    lib.vbk_batch_launches.restype = C.c_longlong
     return lib
 
 

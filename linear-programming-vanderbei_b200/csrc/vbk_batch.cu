@@ -49,12 +49,16 @@ void install_segv_trace()
 }
 }  // namespace
 
+static std::atomic<long long> g_batch_launches(0);
+extern "C" long long vbk_batch_launches(void) { return g_batch_launches.load(); }
+
 extern "C" int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp_desc* lps, int nstreams)
 {
     if (nlp <= 0) return 0;
     if (nstreams < 1) nstreams = 1;
     if (nstreams > nlp) nstreams = nlp;
     std::atomic<int> next(0), failed(0);
+    g_batch_launches.store(0);
     auto worker = [&]() {
 #ifndef VBK_EMU
         VBK_CUDA(cudaSetDevice(device));
@@ -72,6 +76,7 @@ extern "C" int vbk_solve_batch(int method, int device, int mode, int nlp, vbk_lp
                 ? solver_hsdls(device, mode, d.m, d.n, d.nz, d.iA, d.kA, d.A, d.b, d.c, d.f, d.x, d.y, nullptr)
                 : solver_intpt(device, mode, d.m, d.n, d.nz, d.iA, d.kA, d.A, d.b, d.c, d.f, d.x, d.y, nullptr);
             d.iterations = last_thread_iterations();
+            g_batch_launches.fetch_add(last_thread_launches());
             d.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             double po = d.f, du = d.f;              // solve.c:254-255 (objective of the form the solver saw)
             for (int j = 0; j < d.n; ++j) po += d.c[j] * d.x[j];

@@ -57,6 +57,8 @@ struct Timer {
 };
 
 // everything both METHODs share: the LP on the device, the factor object, launch helpers
+static thread_local long long t_last_launches = 0;   // kernels launched by this thread's last solver_* call
+
 struct Workspace {
     int m, n, nz;
     Kkt kkt;
@@ -115,6 +117,7 @@ struct Workspace {
         x.download(hx, n, st);
         y.download(hy, m, st);
         VBK_CUDA(cudaStreamSynchronize(st));
+        t_last_launches = kkt.stats.kernel_launches + la.launches;
         if (prof) {
             prof->factor_calls = kkt.stats.factor_calls;
             prof->solve_calls = kkt.stats.solve_calls;
@@ -177,6 +180,7 @@ static thread_local bool t_quiet = false;
 static thread_local int t_last_iterations = 0;
 void set_thread_quiet(bool quiet) { t_quiet = quiet; }
 int last_thread_iterations() { return t_last_iterations; }
+long long last_thread_launches() { return t_last_launches; }
 #define VBK_LOG(...) do { if (!t_quiet) std::printf(__VA_ARGS__); } while (0)
 #define VBK_LOG_FLUSH() do { if (!t_quiet) std::fflush(stdout); } while (0)
 

@@ -31,6 +31,7 @@ void set_iteration_limit(int itnlim);
 // iteration count of the last solver_* call made by this thread
 void set_thread_quiet(bool quiet);
 int last_thread_iterations();
+long long last_thread_launches();   // kernels launched by the last solver_* call made by this thread
 
 void set_capture(int iter, double* E, double* D, double* rhs_y, double* rhs_x, double* sol_y, double* sol_x);
 
